@@ -1,0 +1,153 @@
+/*
+ * lps_b200.h — C ABI of the B200-native dense-tableau simplex pivot loop.
+ *
+ * Drop-in boundary: the reference (Toptachamann/Linear_Programming_Solver) has no FFI seam;
+ * its hot path is the Java class `lpsolver.LPState` and the two loops in `lpsolver.LPSolver`
+ * that drive it.  Each entry point below replaces one of those members — the reference
+ * location is cited as file:line under src/main/java/lpsolver/.  A JNI / Panama binding calls
+ * exactly these symbols.  Plain C types only; no exception crosses the
+ * boundary; every function returns an `lps_status` (0 = ok, < 0 = error) and verdicts are data.
+ *
+ * The tableau lives in HBM for the life of the handle as the augmented matrix
+ *     T = [ A | b ]   (m rows)
+ *         [ c | -v ]  (1 row)
+ * in binary64, row-major with a padded pitch.  Arithmetic is IEEE-754 round-to-nearest with a
+ * separately rounded multiply and subtract per cell (no FMA) and true division, mirroring the
+ * reference's one-rounding-per-BigDecimal-operation structure (LPState.java:139-177).
+ *
+ * Thread safety: a handle is single-caller (like LPState); distinct handles are independent.
+ */
+#ifndef LPS_B200_H
+#define LPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPS_ABI_VERSION 1
+
+typedef struct lps_handle_s *lps_handle;
+
+/* return codes */
+typedef enum {
+  LPS_OK = 0,
+  LPS_ERR_INVALID = -1,   /* bad argument (range errors on e / l: Validate.isTrue, LPState.java:288) */
+  LPS_ERR_CUDA = -2,      /* CUDA runtime failure; text in lps_last_error */
+  LPS_ERR_STATE = -3,     /* call made in the wrong state (e.g. nothing loaded) */
+  LPS_ERR_NOMEM = -4,
+  LPS_ERR_NODEVICE = -5,  /* no usable CUDA device: there is no CPU fallback */
+  LPS_ERR_COMM = -6       /* multi-GPU exchange failure */
+} lps_status;
+
+/* verdict of lps_run (data, not errors) */
+typedef enum {
+  LPS_RUNNING = 0,
+  LPS_OPTIMAL = 1,    /* getEntering() == -1                      LPSolver.java:101 */
+  LPS_UNBOUNDED = 2,  /* getLeaving(e) == -1                      LPSolver.java:103-106, :147-150 */
+  LPS_PIVOT_CAP = 3   /* max_pivots reached with a pivot pending  (no reference analogue) */
+} lps_verdict;
+
+typedef struct {
+  double epsilon;       /* LPState.DEF_EPSILON = 1e-9   LPState.java:20 */
+  double inf;           /* LPState.DEF_INF     = 1e50   LPState.java:21 */
+  int device;           /* CUDA device ordinal, -1 = current device */
+  int time_kernels;     /* != 0: bracket every tableau-update launch with CUDA events */
+  void *stream;         /* cudaStream_t to run on, NULL = the handle creates its own */
+  int update_variant;   /* tableau-update kernel: 0 = default, >0 selects an alternative (tuning) */
+  int reserved[7];
+} lps_options;
+
+typedef struct {
+  int verdict;          /* lps_verdict */
+  int last_entering;    /* entering index of the last pivot considered (-1 if none) */
+  int last_leaving;
+  int pad_;
+  int64_t npivots;      /* pivots executed by this call */
+  int64_t total_pivots; /* pivots executed on this handle since the last load */
+  double v;             /* objective value after the call (LPState.v) */
+  float device_ms;      /* CUDA-event time of the whole call on the handle's stream */
+  float update_ms;      /* sum of tableau-update kernel times (time_kernels only) */
+  int64_t update_launches;
+  int64_t kernel_launches; /* every kernel this call launched */
+} lps_run_result;
+
+/* one step of LPSolver.restoreInitialLP's objective rebuild (LPSolver.java:217-233) */
+typedef struct {
+  int kind;     /* 0: basic variable  -> v += b[index]*coef ; c[j] += (-A[index][j])*coef  (:223-227)
+                   1: non-basic       -> c[index] += coef                                   (:231) */
+  int index;    /* row (kind 0) or column (kind 1) in the tableau AFTER the column drop */
+  double coef;  /* the variable's coefficient in the initial objective */
+} lps_objective_op;
+
+int lps_abi_version(void);
+void lps_default_options(lps_options *opts);
+const char *lps_status_string(int status);
+
+/* life cycle ------------------------------------------------------------------------------ */
+int lps_create(lps_handle *out, const lps_options *opts);
+int lps_destroy(lps_handle h);
+const char *lps_last_error(lps_handle h); /* valid until the next call on h */
+
+/* LPState(A, b, c, v, …, m, n)  — LPState.java:37-112.  Host buffers are COPIED to HBM (the
+ * reference aliases them, LPSolver.java:267,270; the shim writes results back if it wants the
+ * aliasing).  A is row-major with leading dimension lda >= n. */
+int lps_load(lps_handle h, int m, int n, const double *A, int64_t lda, const double *b,
+             const double *c, double v);
+
+/* LPSolver.convertIntoAuxLP — LPSolver.java:283-321: loads A into an m x (n+1) tableau whose
+ * last column is -1, objective (0,…,0,-1), v = 0.  x0 is variable id n at position n. */
+int lps_load_aux(lps_handle h, int m, int n, const double *A, int64_t lda, const double *b);
+
+/* synthetic dense LP generated directly in HBM (bench / tests):
+ * A_ij = u(i*n+j), c_j = ±u(mn+j), b_i = (n/4)(1+u(mn+n+i)).  rows [row0,row1) only are
+ * materialised when the handle is a row shard (row0=0,row1=m for a single GPU). */
+int lps_generate_dense(lps_handle h, int m, int n, uint64_t seed, int pos_permille);
+
+/* LPState.getEntering() — LPState.java:274-285.  *e = -1 when no c[i] > epsilon. */
+int lps_get_entering(lps_handle h, int *e);
+/* LPState.getLeaving(int) — LPState.java:287-305.  *l = -1 when no ratio < INF. */
+int lps_get_leaving(lps_handle h, int e, int *l);
+/* LPState.pivot(int,int) — LPState.java:114-181 (and exchangeIndexes :311-320). */
+int lps_pivot(lps_handle h, int e, int l);
+
+/* The loops of LPSolver.simplex (LPSolver.java:101-112) and LPSolver.solveAuxLP (:141-161)
+ * run on the device: getEntering / getLeaving / pivot until optimal, unbounded or max_pivots
+ * (< 0 = unlimited) further pivots.  The host is not in the per-pivot path. */
+int lps_run(lps_handle h, int64_t max_pivots, lps_run_result *res);
+
+/* field reads (LPSolver reads LPState.A/b/c/v directly: LPSolver.java:113,170,185,203-245) */
+int lps_dims(lps_handle h, int *m, int *n);
+int lps_read_v(lps_handle h, double *v);
+int lps_read_b(lps_handle h, double *b);            /* m values */
+int lps_read_c(lps_handle h, double *c);            /* n values */
+int lps_read_row(lps_handle h, int i, double *row); /* n values of A[i] */
+int lps_read_col(lps_handle h, int j, double *col); /* m values of A[.][j] */
+int lps_read_A(lps_handle h, double *A, int64_t lda);
+/* variables / coefficients maps (LPState.java:27-28) as a permutation: pos2var[pos] = id of
+ * the variable at position pos (0..n-1 non-basic columns, n..n+m-1 basic rows). */
+int lps_read_positions(lps_handle h, int *pos2var);
+int lps_position_of(lps_handle h, int var, int *pos);
+/* (entering, leaving) pairs since the last load, oldest first; *count = pairs available */
+int lps_read_pivot_log(lps_handle h, int *pairs, int64_t cap_pairs, int64_t *count);
+/* primal values of variables 0..nvars-1: b[pos-n] if basic else 0 (io_files/output.txt:214-233) */
+int lps_read_primal(lps_handle h, int nvars, double *x);
+
+/* phase-1 support (LPSolver.java:166-246) */
+/* performDegeneratePivot's scan — LPSolver.java:185-191: first j with |A[row][j]| > epsilon */
+int lps_first_nonzero_in_row(lps_handle h, int row, int *j);
+/* restoreInitialLP — LPSolver.java:205-211,235-244: remove column j (positions shift down) */
+int lps_drop_column(lps_handle h, int j);
+/* restoreInitialLP — LPSolver.java:213-233: c <- 0, v <- 0, then apply ops in order */
+int lps_rebuild_objective(lps_handle h, const lps_objective_op *ops, int nops);
+
+/* introspection */
+int lps_device_info(lps_handle h, int *sm_count, int64_t *hbm_bytes, int *cc_major, int *cc_minor);
+int lps_tableau_bytes(lps_handle h, int64_t *bytes);     /* 8*(m+1)*pitch */
+int lps_algorithmic_bytes_per_pivot(lps_handle h, int64_t *bytes); /* 16*(m+1)*(n+1) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPS_B200_H */

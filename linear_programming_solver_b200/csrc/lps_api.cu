@@ -1,0 +1,691 @@
+// C-ABI implementation (include/lps_b200.h) over the kernels in lps_kernels.cuh.
+// Host responsibilities only: allocation, host<->HBM copies, launch sequencing in batches,
+// polling of the device control block.  No arithmetic on tableau values happens on the host
+// and there is no CPU fallback: without a CUDA device every entry point fails.
+#include "../../include/lps_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lps_kernels.cuh"
+
+using namespace lps;
+
+struct lps_handle_s {
+  lps_options opt;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+
+  bool loaded = false;
+  int m = 0, n = 0;
+  long long ld = 0;
+  double* T = nullptr;
+  size_t T_bytes = 0;
+  double *col0 = nullptr, *col1 = nullptr, *bcol = nullptr, *rowbuf = nullptr, *scratch = nullptr;
+  size_t vec_cap = 0;  // capacity (doubles) of col0/col1/bcol/scratch; rowbuf has its own
+  size_t row_cap = 0;
+  int* pos2var = nullptr;
+  size_t pos_cap = 0;
+  int2* plog = nullptr;
+  long long log_cap = 1ll << 22;
+  Ctl* ctl = nullptr;
+  Ctl* h_ctl = nullptr;  // pinned
+  Cand* partials = nullptr;
+  ObjOp* d_ops = nullptr;
+  size_t ops_cap = 0;
+
+  // device-side (e_next, colbuf[npivots&1], bcol) are consistent with the tableau
+  bool next_valid = false;
+  // colbuf[npivots&1] holds this column (or -1)
+  int col_holds = -1;
+  long long total_pivots = 0;
+
+  std::vector<cudaEvent_t> ev;  // time_kernels event pool
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  std::string err;
+};
+
+namespace {
+
+constexpr int kRatioThreads = 256;
+
+int fail(lps_handle h, int code, const char* what, cudaError_t ce = cudaSuccess) {
+  if (h) {
+    h->err = what;
+    if (ce != cudaSuccess) {
+      h->err += ": ";
+      h->err += cudaGetErrorString(ce);
+    }
+  }
+  return code;
+}
+
+#define CK(call)                                                     \
+  do {                                                               \
+    cudaError_t ce_ = (call);                                        \
+    if (ce_ != cudaSuccess) return fail(h, LPS_ERR_CUDA, #call, ce_); \
+  } while (0)
+
+inline long long round_up(long long x, long long a) { return (x + a - 1) / a * a; }
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int free_tableau(lps_handle h) {
+  if (h->T) cudaFree(h->T);
+  h->T = nullptr;
+  h->T_bytes = 0;
+  return 0;
+}
+
+int ensure_buffers(lps_handle h, int m, int n_cols /* n incl. any aux column */) {
+  long long ld = round_up((long long)n_cols + 1, 16);
+  size_t need = (size_t)(m + 1) * (size_t)ld * sizeof(double);
+  if (need > h->T_bytes) {
+    free_tableau(h);
+    cudaError_t ce = cudaMalloc(&h->T, need);
+    if (ce != cudaSuccess) return fail(h, LPS_ERR_NOMEM, "cudaMalloc(tableau)", ce);
+    h->T_bytes = need;
+  }
+  size_t vneed = (size_t)m + 1 + 16;
+  if (vneed > h->vec_cap) {
+    for (double** p : {&h->col0, &h->col1, &h->bcol, &h->scratch}) {
+      if (*p) cudaFree(*p);
+      cudaError_t ce = cudaMalloc(p, vneed * sizeof(double));
+      if (ce != cudaSuccess) return fail(h, LPS_ERR_NOMEM, "cudaMalloc(column staging)", ce);
+    }
+    h->vec_cap = vneed;
+  }
+  if ((size_t)ld > h->row_cap) {
+    if (h->rowbuf) cudaFree(h->rowbuf);
+    cudaError_t ce = cudaMalloc(&h->rowbuf, (size_t)ld * sizeof(double));
+    if (ce != cudaSuccess) return fail(h, LPS_ERR_NOMEM, "cudaMalloc(row staging)", ce);
+    h->row_cap = (size_t)ld;
+  }
+  size_t pneed = (size_t)m + n_cols + 16;
+  if (pneed > h->pos_cap) {
+    if (h->pos2var) cudaFree(h->pos2var);
+    cudaError_t ce = cudaMalloc(&h->pos2var, pneed * sizeof(int));
+    if (ce != cudaSuccess) return fail(h, LPS_ERR_NOMEM, "cudaMalloc(positions)", ce);
+    h->pos_cap = pneed;
+  }
+  h->m = m;
+  h->n = n_cols;
+  h->ld = ld;
+  return LPS_OK;
+}
+
+int reset_state(lps_handle h) {
+  CK(cudaMemsetAsync(h->ctl, 0, sizeof(Ctl), h->stream));
+  int tot = h->m + h->n;
+  k_iota<<<cdiv(tot, 256), 256, 0, h->stream>>>(h->pos2var, tot);
+  CK(cudaGetLastError());
+  h->next_valid = false;
+  h->col_holds = -1;
+  h->total_pivots = 0;
+  h->loaded = true;
+  return LPS_OK;
+}
+
+int sync_ctl(lps_handle h) {
+  CK(cudaMemcpyAsync(h->h_ctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return LPS_OK;
+}
+
+int ratio_grid(lps_handle h) {
+  return std::max(1, std::min(cdiv(h->m, kRatioThreads), 2 * h->sm_count));
+}
+
+// launch K2 + K3 for the pivot already committed in ctl
+int launch_scale_update(lps_handle h, cudaEvent_t e0, cudaEvent_t e1) {
+  k_scale_row<<<cdiv(h->ld, 256), 256, 0, h->stream>>>(h->ctl, h->T, h->ld, h->m, h->n, h->rowbuf,
+                                                      h->col0, h->col1, h->opt.epsilon);
+  if (e0) cudaEventRecord(e0, h->stream);
+#define LPS_UPD(T_, R_, U_, B_)                                                               \
+  do {                                                                                        \
+    dim3 grid(cdiv(h->ld, 4ll * (T_)), cdiv(h->m + 1, (R_)));                                 \
+    k_update<T_, R_, U_, B_><<<grid, (T_), 0, h->stream>>>(h->ctl, h->T, h->ld, h->m, h->n,   \
+                                                          h->rowbuf, h->col0, h->col1, h->bcol); \
+  } while (0)
+  switch (h->opt.update_variant) {
+    default:
+    case 0: LPS_UPD(256, 32, 8, 1); break;
+    case 1: LPS_UPD(256, 32, 4, 2); break;
+    case 2: LPS_UPD(256, 64, 8, 1); break;
+    case 3: LPS_UPD(128, 32, 8, 2); break;
+    case 4: LPS_UPD(512, 32, 4, 1); break;
+    case 5: LPS_UPD(256, 32, 8, 2); break;
+    case 6: LPS_UPD(128, 64, 4, 4); break;
+    case 7: LPS_UPD(256, 16, 4, 3); break;
+  }
+#undef LPS_UPD
+  if (e1) cudaEventRecord(e1, h->stream);
+  return LPS_OK;
+}
+
+int launch_ratio(lps_handle h, int mode) {
+  k_ratio<<<ratio_grid(h), kRatioThreads, 0, h->stream>>>(h->ctl, h->col0, h->col1, h->bcol, h->m,
+                                                         h->n, h->opt.epsilon, h->opt.inf,
+                                                         h->partials, h->plog, h->log_cap,
+                                                         h->pos2var, mode);
+  return LPS_OK;
+}
+
+// make (e_next, colbuf, bcol) valid on the device
+int prepare_next(lps_handle h) {
+  if (h->next_valid) return LPS_OK;
+  k_begin_run<<<1, 1, 0, h->stream>>>(h->ctl, -1, 1);
+  k_first_positive<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->ctl, h->T + (long long)h->m * h->ld,
+                                                          h->n, h->opt.epsilon);
+  k_extract<<<cdiv(h->m + 1, 256), 256, 0, h->stream>>>(h->ctl, h->T, h->ld, h->m, h->n, -1, h->col0,
+                                                       h->col1, h->bcol);
+  CK(cudaGetLastError());
+  h->next_valid = true;
+  h->col_holds = -2;  // "whatever e_next is"
+  return LPS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lps_abi_version(void) { return LPS_ABI_VERSION; }
+
+void lps_default_options(lps_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->epsilon = 1e-9;
+  o->inf = 1e50;
+  o->device = -1;
+}
+
+const char* lps_status_string(int s) {
+  switch (s) {
+    case LPS_OK: return "ok";
+    case LPS_ERR_INVALID: return "invalid argument";
+    case LPS_ERR_CUDA: return "CUDA error";
+    case LPS_ERR_STATE: return "call in wrong state";
+    case LPS_ERR_NOMEM: return "out of device memory";
+    case LPS_ERR_NODEVICE: return "no CUDA device (there is no CPU fallback)";
+    case LPS_ERR_COMM: return "multi-GPU exchange failure";
+    default: return "unknown";
+  }
+}
+
+int lps_create(lps_handle* out, const lps_options* opts) {
+  if (!out) return LPS_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return LPS_ERR_NODEVICE;
+  lps_handle h = new (std::nothrow) lps_handle_s();
+  if (!h) return LPS_ERR_NOMEM;
+  if (opts) h->opt = *opts; else lps_default_options(&h->opt);
+  if (h->opt.device >= 0) {
+    if (h->opt.device >= ndev) { delete h; return LPS_ERR_INVALID; }
+    h->dev = h->opt.device;
+  } else {
+    cudaGetDevice(&h->dev);
+  }
+  cudaError_t ce = cudaSetDevice(h->dev);
+  if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev);
+  if (ce == cudaSuccess) {
+    if (h->opt.stream) {
+      h->stream = (cudaStream_t)h->opt.stream;
+    } else {
+      ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+      h->own_stream = true;
+    }
+  }
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->ctl, sizeof(Ctl));
+  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_ctl, sizeof(Ctl));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->partials, 4096 * sizeof(Cand));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->plog, (size_t)h->log_cap * sizeof(int2));
+  if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev_begin);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev_end);
+  if (ce != cudaSuccess) {
+    lps_destroy(h);
+    return LPS_ERR_CUDA;
+  }
+  *out = h;
+  return LPS_OK;
+}
+
+int lps_destroy(lps_handle h) {
+  if (!h) return LPS_OK;
+  cudaSetDevice(h->dev);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_tableau(h);
+  for (double* p : {h->col0, h->col1, h->bcol, h->scratch, h->rowbuf}) if (p) cudaFree(p);
+  if (h->pos2var) cudaFree(h->pos2var);
+  if (h->plog) cudaFree(h->plog);
+  if (h->ctl) cudaFree(h->ctl);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->partials) cudaFree(h->partials);
+  if (h->d_ops) cudaFree(h->d_ops);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+  if (h->ev_end) cudaEventDestroy(h->ev_end);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return LPS_OK;
+}
+
+const char* lps_last_error(lps_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+static int load_common(lps_handle h, int m, int n_src, int n_cols, const double* A, int64_t lda,
+                       const double* b, const double* c, double v, bool aux) {
+  if (!h) return LPS_ERR_INVALID;
+  if (m < 0 || n_src < 0 || (m > 0 && n_src > 0 && !A) || (m > 0 && !b) || lda < n_src)
+    return fail(h, LPS_ERR_INVALID, "lps_load: bad dimensions or null buffer");
+  CK(cudaSetDevice(h->dev));
+  int rc = ensure_buffers(h, m, n_cols);
+  if (rc) return rc;
+  const long long ld = h->ld;
+  CK(cudaMemsetAsync(h->T, 0, (size_t)(m + 1) * ld * sizeof(double), h->stream));
+  if (m > 0 && n_src > 0)
+    CK(cudaMemcpy2DAsync(h->T, ld * sizeof(double), A, (size_t)lda * sizeof(double),
+                         (size_t)n_src * sizeof(double), m, cudaMemcpyHostToDevice, h->stream));
+  if (m > 0) {
+    CK(cudaMemcpyAsync(h->scratch, b, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_set_column<<<cdiv(m, 256), 256, 0, h->stream>>>(h->T, ld, m, n_cols, h->scratch, 0.0, 0);
+  }
+  if (aux) {
+    if (m > 0) k_set_column<<<cdiv(m, 256), 256, 0, h->stream>>>(h->T, ld, m, n_src, nullptr, -1.0, 1);
+    const double minus1 = -1.0;  // c_aux = (0,…,0,-1)
+    CK(cudaMemcpyAsync(h->T + (long long)m * ld + n_src, &minus1, sizeof(double),
+                       cudaMemcpyHostToDevice, h->stream));
+  } else {
+    if (n_src > 0)
+      CK(cudaMemcpyAsync(h->T + (long long)m * ld, c, (size_t)n_src * sizeof(double),
+                         cudaMemcpyHostToDevice, h->stream));
+    const double negv = -v;
+    CK(cudaMemcpyAsync(h->T + (long long)m * ld + n_cols, &negv, sizeof(double),
+                       cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaGetLastError());
+  rc = reset_state(h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return LPS_OK;
+}
+
+int lps_load(lps_handle h, int m, int n, const double* A, int64_t lda, const double* b,
+             const double* c, double v) {
+  if (h && n > 0 && !c) return fail(h, LPS_ERR_INVALID, "lps_load: null c");
+  return load_common(h, m, n, n, A, lda, b, c, v, false);
+}
+
+int lps_load_aux(lps_handle h, int m, int n, const double* A, int64_t lda, const double* b) {
+  return load_common(h, m, n, n + 1, A, lda, b, nullptr, 0.0, true);
+}
+
+int lps_generate_dense(lps_handle h, int m, int n, uint64_t seed, int pos_permille) {
+  if (!h || m <= 0 || n <= 0) return fail(h, LPS_ERR_INVALID, "lps_generate_dense: bad dimensions");
+  CK(cudaSetDevice(h->dev));
+  int rc = ensure_buffers(h, m, n);
+  if (rc) return rc;
+  dim3 grid(std::min(cdiv(h->ld, 256), 64), std::min(m + 1, 65535));
+  k_generate_dense<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m, n, seed, pos_permille);
+  CK(cudaGetLastError());
+  rc = reset_state(h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return LPS_OK;
+}
+
+int lps_get_entering(lps_handle h, int* e) {
+  if (!h || !e) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  int rc = prepare_next(h);
+  if (rc) return rc;
+  rc = sync_ctl(h);
+  if (rc) return rc;
+  *e = (h->h_ctl->e_next == kNone) ? -1 : h->h_ctl->e_next;
+  return LPS_OK;
+}
+
+int lps_get_leaving(lps_handle h, int e, int* l) {
+  if (!h || !l) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  if (e < 0 || e >= h->n) return fail(h, LPS_ERR_INVALID, "getLeaving: entering out of range");
+  CK(cudaSetDevice(h->dev));
+  // stage column e and b; this invalidates the loop's staged (e_next, column) pair unless e is it
+  k_extract<<<cdiv(h->m + 1, 256), 256, 0, h->stream>>>(h->ctl, h->T, h->ld, h->m, h->n, e, h->col0,
+                                                       h->col1, h->bcol);
+  h->next_valid = false;
+  h->col_holds = e;
+  launch_ratio(h, 1);
+  CK(cudaGetLastError());
+  int rc = sync_ctl(h);
+  if (rc) return rc;
+  *l = h->h_ctl->q_leaving;
+  return LPS_OK;
+}
+
+int lps_pivot(lps_handle h, int e, int l) {
+  if (!h) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  if (e < 0 || e >= h->n || l < 0 || l >= h->m)
+    return fail(h, LPS_ERR_INVALID, "pivot: index out of range");
+  CK(cudaSetDevice(h->dev));
+  if (h->col_holds != e) {
+    k_extract<<<cdiv(h->m + 1, 256), 256, 0, h->stream>>>(h->ctl, h->T, h->ld, h->m, h->n, e,
+                                                         h->col0, h->col1, h->bcol);
+  }
+  k_set_pivot<<<1, 1, 0, h->stream>>>(h->ctl, h->col0, h->col1, e, l, h->n, h->plog, h->log_cap,
+                                      h->pos2var);
+  launch_scale_update(h, nullptr, nullptr);
+  CK(cudaGetLastError());
+  int rc = sync_ctl(h);
+  if (rc) return rc;
+  if (h->h_ctl->status == kZeroPivot) {
+    h->next_valid = false;
+    h->col_holds = -1;
+    return fail(h, LPS_ERR_INVALID, "pivot: pivot element is zero (ArithmeticException in the reference)");
+  }
+  h->total_pivots = h->h_ctl->npivots;
+  h->next_valid = true;  // k_scale_row/k_update staged the next entering column
+  h->col_holds = -2;
+  return LPS_OK;
+}
+
+int lps_run(lps_handle h, int64_t max_pivots, lps_run_result* res) {
+  if (!h) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  const long long start_pivots = h->total_pivots;
+  long long launches = 0;
+  CK(cudaEventRecord(h->ev_begin, h->stream));
+  int rc = prepare_next(h);
+  if (rc) return rc;
+  launches += 3;
+  k_begin_run<<<1, 1, 0, h->stream>>>(h->ctl, max_pivots, 0);
+  launches++;
+
+  // batch size: about 30 ms of device work per host check, from the tableau's size
+  const double bytes = 16.0 * (double)(h->m + 1) * (double)(h->n + 1);
+  const double est_us = bytes / 5.0e6 + 12.0;  // ~5 TB/s + fixed launch chain
+  long long batch = (long long)(30000.0 / est_us);
+  batch = std::max(8ll, std::min(batch, 4096ll));
+  const bool timed = h->opt.time_kernels != 0;
+  if (timed) {
+    while ((long long)h->ev.size() < 2 * batch) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->ev.push_back(e);
+    }
+  }
+  double upd_ms = 0.0;
+  long long upd_launches = 0;
+  long long remaining = (max_pivots < 0) ? -1 : (long long)max_pivots;
+  for (;;) {
+    // one extra ratio step past the cap is what turns "cap reached" into a verdict
+    long long todo = (remaining < 0) ? batch : std::min(batch, remaining + 1);
+    for (long long k = 0; k < todo; k++) {
+      launch_ratio(h, 0);
+      launch_scale_update(h, timed ? h->ev[2 * k] : nullptr, timed ? h->ev[2 * k + 1] : nullptr);
+    }
+    launches += 3 * todo;
+    CK(cudaGetLastError());
+    rc = sync_ctl(h);
+    if (rc) return rc;
+    long long done_now = h->h_ctl->npivots - h->total_pivots;
+    if (timed) {
+      for (long long k = 0; k < done_now && k < todo; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[2 * k], h->ev[2 * k + 1]) == cudaSuccess) upd_ms += ms;
+        upd_launches++;
+      }
+    }
+    h->total_pivots = h->h_ctl->npivots;
+    if (remaining >= 0) remaining -= done_now;
+    if (h->h_ctl->status != kRunning) break;
+  }
+  CK(cudaEventRecord(h->ev_end, h->stream));
+  CK(cudaEventSynchronize(h->ev_end));
+  // after a terminal verdict the staged (e_next, column) pair is still the one the verdict was
+  // taken on, so a later call may continue from it (e.g. after PIVOT_CAP)
+  h->next_valid = (h->h_ctl->status == kPivotCap);
+  h->col_holds = h->next_valid ? -2 : -1;
+  if (res) {
+    std::memset(res, 0, sizeof(*res));
+    res->verdict = h->h_ctl->status;
+    res->last_entering = h->h_ctl->e_cur;
+    res->last_leaving = h->h_ctl->l_cur;
+    res->npivots = h->total_pivots - start_pivots;
+    res->total_pivots = h->total_pivots;
+    double corner = 0.0;
+    CK(cudaMemcpy(&corner, h->T + (long long)h->m * h->ld + h->n, sizeof(double), cudaMemcpyDeviceToHost));
+    res->v = 0.0 - corner;
+    cudaEventElapsedTime(&res->device_ms, h->ev_begin, h->ev_end);
+    res->update_ms = (float)upd_ms;
+    res->update_launches = upd_launches;
+    res->kernel_launches = launches;
+  }
+  return LPS_OK;
+}
+
+int lps_dims(lps_handle h, int* m, int* n) {
+  if (!h || !h->loaded) return LPS_ERR_STATE;
+  if (m) *m = h->m;
+  if (n) *n = h->n;
+  return LPS_OK;
+}
+
+int lps_read_v(lps_handle h, double* v) {
+  if (!h || !v) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  CK(cudaStreamSynchronize(h->stream));
+  double corner = 0.0;
+  CK(cudaMemcpy(&corner, h->T + (long long)h->m * h->ld + h->n, sizeof(double), cudaMemcpyDeviceToHost));
+  *v = 0.0 - corner;
+  return LPS_OK;
+}
+
+static int read_column(lps_handle h, int col, double* dst) {
+  if (h->m == 0) return LPS_OK;
+  k_gather_column<<<cdiv(h->m, 256), 256, 0, h->stream>>>(h->T, h->ld, h->m, col, h->scratch);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst, h->scratch, (size_t)h->m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return LPS_OK;
+}
+
+int lps_read_b(lps_handle h, double* b) {
+  if (!h || !b) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  return read_column(h, h->n, b);
+}
+
+int lps_read_col(lps_handle h, int j, double* col) {
+  if (!h || !col) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  if (j < 0 || j >= h->n) return fail(h, LPS_ERR_INVALID, "read_col: column out of range");
+  CK(cudaSetDevice(h->dev));
+  return read_column(h, j, col);
+}
+
+int lps_read_c(lps_handle h, double* c) {
+  if (!h || !c) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->n > 0)
+    CK(cudaMemcpy(c, h->T + (long long)h->m * h->ld, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost));
+  return LPS_OK;
+}
+
+int lps_read_row(lps_handle h, int i, double* row) {
+  if (!h || !row) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  if (i < 0 || i >= h->m) return fail(h, LPS_ERR_INVALID, "read_row: row out of range");
+  CK(cudaSetDevice(h->dev));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->n > 0)
+    CK(cudaMemcpy(row, h->T + (long long)i * h->ld, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost));
+  return LPS_OK;
+}
+
+int lps_read_A(lps_handle h, double* A, int64_t lda) {
+  if (!h || !A || lda < (h ? h->n : 0)) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->m > 0 && h->n > 0)
+    CK(cudaMemcpy2D(A, (size_t)lda * sizeof(double), h->T, (size_t)h->ld * sizeof(double),
+                    (size_t)h->n * sizeof(double), h->m, cudaMemcpyDeviceToHost));
+  return LPS_OK;
+}
+
+int lps_read_positions(lps_handle h, int* pos2var) {
+  if (!h || !pos2var) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(pos2var, h->pos2var, (size_t)(h->m + h->n) * sizeof(int), cudaMemcpyDeviceToHost));
+  return LPS_OK;
+}
+
+int lps_position_of(lps_handle h, int var, int* pos) {
+  if (!h || !pos) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  std::vector<int> p((size_t)h->m + h->n);
+  int rc = lps_read_positions(h, p.data());
+  if (rc) return rc;
+  *pos = -1;
+  for (size_t k = 0; k < p.size(); k++)
+    if (p[k] == var) { *pos = (int)k; break; }
+  return LPS_OK;
+}
+
+int lps_read_pivot_log(lps_handle h, int* pairs, int64_t cap_pairs, int64_t* count) {
+  if (!h || !count) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  CK(cudaStreamSynchronize(h->stream));
+  long long total = h->total_pivots;
+  long long avail = std::min(total, h->log_cap);
+  *count = avail;
+  if (!pairs || cap_pairs <= 0) return LPS_OK;
+  long long take = std::min<long long>(avail, cap_pairs);
+  long long first = total - avail;  // oldest retained pivot
+  for (long long k = 0; k < take;) {
+    long long slot = (first + k) % h->log_cap;
+    long long run = std::min(take - k, h->log_cap - slot);
+    CK(cudaMemcpy(pairs + 2 * k, h->plog + slot, (size_t)run * sizeof(int2), cudaMemcpyDeviceToHost));
+    k += run;
+  }
+  return LPS_OK;
+}
+
+int lps_read_primal(lps_handle h, int nvars, double* x) {
+  if (!h || !x || nvars < 0) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  std::vector<int> p((size_t)h->m + h->n);
+  std::vector<double> b((size_t)h->m);
+  int rc = lps_read_positions(h, p.data());
+  if (rc) return rc;
+  rc = lps_read_b(h, b.data());
+  if (rc) return rc;
+  for (int k = 0; k < nvars; k++) x[k] = 0.0;
+  for (int pos = h->n; pos < h->n + h->m; pos++) {
+    int var = p[pos];
+    if (var >= 0 && var < nvars) x[var] = b[pos - h->n];
+  }
+  return LPS_OK;
+}
+
+int lps_first_nonzero_in_row(lps_handle h, int row, int* j) {
+  if (!h || !j) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  if (row < 0 || row >= h->m) return fail(h, LPS_ERR_INVALID, "first_nonzero_in_row: row out of range");
+  CK(cudaSetDevice(h->dev));
+  const int none = kNone;
+  CK(cudaMemcpyAsync(&h->ctl->q_index, &none, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  k_first_nonzero<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->ctl, h->T + (long long)row * h->ld, h->n,
+                                                         h->opt.epsilon);
+  CK(cudaGetLastError());
+  int rc = sync_ctl(h);
+  if (rc) return rc;
+  *j = (h->h_ctl->q_index == kNone) ? -1 : h->h_ctl->q_index;
+  return LPS_OK;
+}
+
+int lps_drop_column(lps_handle h, int j) {
+  if (!h) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  if (j < 0 || j >= h->n) return fail(h, LPS_ERR_INVALID, "drop_column: column out of range");
+  CK(cudaSetDevice(h->dev));
+  const int threads = 256;
+  int grid = std::min(h->m + 1, 8 * h->sm_count);
+  k_drop_column<<<grid, threads, 0, h->stream>>>(h->T, h->ld, h->m, h->n, j);
+  CK(cudaGetLastError());
+  // positions j+1.. shift down by one (LPSolver.java:239-244)
+  std::vector<int> p((size_t)h->m + h->n);
+  CK(cudaMemcpyAsync(p.data(), h->pos2var, p.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  p.erase(p.begin() + j);
+  CK(cudaMemcpy(h->pos2var, p.data(), p.size() * sizeof(int), cudaMemcpyHostToDevice));
+  h->n -= 1;
+  h->next_valid = false;
+  h->col_holds = -1;
+  return LPS_OK;
+}
+
+int lps_rebuild_objective(lps_handle h, const lps_objective_op* ops, int nops) {
+  if (!h || nops < 0 || (nops > 0 && !ops)) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  for (int k = 0; k < nops; k++) {
+    if (ops[k].kind == 0 ? (ops[k].index < 0 || ops[k].index >= h->m)
+                         : (ops[k].kind != 1 || ops[k].index < 0 || ops[k].index >= h->n))
+      return fail(h, LPS_ERR_INVALID, "rebuild_objective: op index out of range");
+  }
+  CK(cudaSetDevice(h->dev));
+  if ((size_t)nops > h->ops_cap) {
+    if (h->d_ops) cudaFree(h->d_ops);
+    h->ops_cap = (size_t)nops + 64;
+    CK(cudaMalloc(&h->d_ops, h->ops_cap * sizeof(ObjOp)));
+  }
+  static_assert(sizeof(ObjOp) == sizeof(lps_objective_op), "op layout");
+  if (nops > 0)
+    CK(cudaMemcpyAsync(h->d_ops, ops, (size_t)nops * sizeof(ObjOp), cudaMemcpyHostToDevice, h->stream));
+  k_rebuild_objective<<<cdiv(h->n + 1, 128), 128, 0, h->stream>>>(h->T, h->ld, h->m, h->n, h->d_ops, nops);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->next_valid = false;
+  h->col_holds = -1;
+  return LPS_OK;
+}
+
+int lps_device_info(lps_handle h, int* sm_count, int64_t* hbm_bytes, int* cc_major, int* cc_minor) {
+  if (!h) return LPS_ERR_INVALID;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (hbm_bytes) *hbm_bytes = (int64_t)prop.totalGlobalMem;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return LPS_OK;
+}
+
+int lps_tableau_bytes(lps_handle h, int64_t* bytes) {
+  if (!h || !bytes || !h->loaded) return LPS_ERR_STATE;
+  *bytes = (int64_t)sizeof(double) * (h->m + 1) * h->ld;
+  return LPS_OK;
+}
+
+int lps_algorithmic_bytes_per_pivot(lps_handle h, int64_t* bytes) {
+  if (!h || !bytes || !h->loaded) return LPS_ERR_STATE;
+  *bytes = 16ll * (h->m + 1) * (h->n + 1);
+  return LPS_OK;
+}
+
+}  // extern "C"
