@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — pivots/s and tableau-update HBM GB/s of the simplex pivot loop on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): synthetic
+dense LP, 20,000 constraints x 40,000 variables, max with <= rows (SURVEY.md §8d generator,
+seed 0), FP64 tableau of 6.4 GB resident in HBM.  One *step* = `--pivots-per-step` pivots of
+the running solve (getEntering / getLeaving / pivot on the device, LPSolver.java:101-112).
+
+The JSON line carries, beside the contract keys:
+  value      pivots/s, whole job, inputs already in HBM, CUDA-event time on the library's
+             stream (max over ranks)
+  e2e        the same metric through the reference-facing call path with HOST buffers:
+             lps_load (H2D of the whole tableau from pinned memory) + run + read-back of
+             b, c, v and the position map, wall clock around synchronous calls
+  roofline   tableau-update kernel: algorithmic bytes 16(m+1)(n+1) per launch / its mean
+             CUDA-event duration over the timed region, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle's C binary64 twin of LPState.pivotConcurrently (kind "port";
+             the Java reference cannot run: no JVM) on the box's host cores, bounded sample
+
+`--impl reference` times that CPU port alone on the same config (all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pivots_per_sec"
+UNIT = "pivots/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=int, default=20000)
+    ap.add_argument("--n", type=int, default=40000)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--pivots-per-step", type=int, default=50)
+    ap.add_argument("--e2e-pivots", type=int, default=200)
+    ap.add_argument("--cpu-pivots", type=int, default=0, help="0 = sized for ~10-30 s")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variant", type=int, default=-1)
+    return ap.parse_args()
+
+
+def workload_name(m, n):
+    return "synthetic dense LP %dx%d (max, <= rows, seed-generated, FP64 tableau %.2f GB)" % (
+        m, n, 8.0 * (m + 1) * (n + 1) / 1e9)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_rate(A, b, c, pivots, threads):
+    """pivots/s of the oracle's C twin of pivotConcurrently on host cores (bench-only use of oracle/)."""
+    from oracle import tier_f
+    st = tier_f.TierFState(A, b, c, nthreads=threads)
+    t0 = time.perf_counter()
+    status, k = st.run(pivots)
+    dt = time.perf_counter() - t0
+    return (k / dt if dt > 0 else 0.0), k, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path, all host threads, same config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import tier_f
+    threads = tier_f.lib().tf_max_threads()
+    m, n = args.m, args.n
+    A, b, c = tier_f.gen_dense_feasible(m, n, args.seed, nthreads=threads)
+    st = tier_f.TierFState(A, b, c, nthreads=threads)
+    # one pivot moves 16*m*n bytes through host DRAM: bound a step to ~1-2 s
+    t0 = time.perf_counter()
+    st.run(1)
+    t1 = time.perf_counter() - t0
+    per_step = max(1, min(args.pivots_per_step, int(1.0 / max(t1, 1e-4))))
+    for _ in range(args.warmup):
+        st.run(per_step)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        _, k = st.run(per_step)
+        done += k
+    dt = time.perf_counter() - t0
+    value = done / dt
+    sample = "%d steps x %d pivots of the %dx%d solve (one pivot = %.1f GB of host DRAM traffic)" % (
+        args.steps, per_step, m, n, 16.0 * m * n / 1e9)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_name(m, n), "pivots_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C binary64 port of LPState.pivotConcurrently (oracle/tier_f.c); the Java reference "
+                "cannot run (no JVM in the image); an upper bound on its BigDecimal speed",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    import linear_programming_solver_b200 as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1:
+        from linear_programming_solver_b200 import sharded
+        return sharded.bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_name,
+                                     measured_peak, ClockSampler)
+
+    m, n, P = args.m, args.n, args.pivots_per_step
+    kw = dict(device=local_rank, time_kernels=True)
+    if args.variant >= 0:
+        kw["update_variant"] = args.variant
+    st = L.LPState.synthetic_dense(m, n, args.seed, 1000, **kw)
+    bytes_pp = st.algorithmic_bytes_per_pivot()
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        st.run(P)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms, upd_ms, upd_n, launches, pivots = 0.0, 0.0, 0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = st.run(P)
+        dev_ms += r.device_ms
+        upd_ms += r.update_ms
+        upd_n += r.update_launches
+        launches += r.kernel_launches
+        pivots += r.npivots
+        if r.verdict != 3:
+            break
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    if pivots != args.steps * P:
+        raise SystemExit("the synthetic LP terminated inside the timed region (%d pivots, verdict %d): "
+                         "pick fewer steps" % (pivots, r.verdict))
+    value = pivots / (dev_ms / 1e3)
+    peak, peak_src = measured_peak()
+    upd_avg_ms = upd_ms / max(upd_n, 1)
+    achieved = bytes_pp / (upd_avg_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(m, n), "pivots_per_step": P, "seed": args.seed,
+                   "l2": "tableau (6.4 GB) is far larger than the 126 MB L2; no flush needed",
+                   "timing": "CUDA events on the library's stream around each step"},
+        "gpu_launches": int(launches),
+        "loop_gbs": bytes_pp * pivots / (dev_ms * 1e-3) / 1e9,
+        "frac_of_8tbs": bytes_pp * pivots / (dev_ms * 1e-3) / 1e9 / 8000.0,
+        "wall_s": wall,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "kernel": "lps::k_update",
+                     "launches": int(upd_n), "avg_ms": upd_avg_ms, "peak_source": peak_src,
+                     "bytes_per_launch": bytes_pp, "frac_of_8tbs": achieved / 8000.0},
+        "clocks": clocks,
+    }
+    st.close()
+
+    # ---- host copy of the same input (untimed): generated on the device, read back ----
+    need_host = not (args.no_e2e and args.no_cpu_baseline)
+    if need_host:
+        from linear_programming_solver_b200.lp_state import _dp
+        A_pin = torch.empty((m, n), dtype=torch.float64, pin_memory=True)
+        A_host = A_pin.numpy()
+        g = L.LPState.synthetic_dense(m, n, args.seed, 1000, device=local_rank)
+        g._ck(g._lib.lps_read_A(g._h, _dp(A_host), n), "read_A")
+        b_host, c_host = g.b, g.c
+        g.close()
+    # ---- e2e: host buffers in, results out, through the reference-facing call sequence ----
+    if not args.no_e2e:
+        Pe = args.e2e_pivots
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s = L.LPState(A_host, b_host, c_host, m, n, device=local_rank)   # H2D of the tableau
+            r = s.run(Pe)
+            out_b, out_c, out_v, out_pos = s.b, s.c, s.v, s.positions         # D2H of the result
+            dt = time.perf_counter() - t0
+            s.close()
+            best = dt if best is None else min(best, dt)
+        line["e2e"] = {"value": Pe / best, "unit": UNIT,
+                       "h2d_bytes_per_step": int(8 * (m * n + m + n)),
+                       "d2h_bytes_per_step": int(8 * (m + n + 1) + 4 * (m + n)),
+                       "pivots_per_call": Pe, "seconds_per_call": best,
+                       "what": "LPState(A,b,c) from pinned host memory + run(%d) + read b,c,v,positions" % Pe}
+    # ---- CPU baseline on the same input (bounded sample) ----
+    if not args.no_cpu_baseline:
+        from oracle import tier_f
+        threads = tier_f.lib().tf_max_threads()
+        A_cpu = np.array(A_host, copy=True)
+        rate1, k1, dt1 = cpu_port_rate(A_cpu, b_host.copy(), c_host.copy(), 2, threads)
+        want = args.cpu_pivots or max(3, min(60, int(15.0 * rate1)))
+        A_cpu[...] = A_host
+        rate, k, dt = cpu_port_rate(A_cpu, b_host.copy(), c_host.copy(), want, threads)
+        line["cpu_baseline"] = {
+            "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "first %d pivots of the same %dx%d LP in %.1f s, C binary64 twin of "
+                      "LPState.pivotConcurrently with %d threads (reference THREAD_AMOUNT is 4)" % (k, m, n, dt, threads)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,10 +153,10 @@ int launch_scale_update(lps_handle h, cudaEvent_t e0, cudaEvent_t e1) {
                                                           h->rowbuf, h->col0, h->col1, h->bcol); \
   } while (0)
   switch (h->opt.update_variant) {
-    default:
     case 0: LPS_UPD(256, 32, 8, 1); break;
     case 1: LPS_UPD(256, 32, 4, 2); break;
     case 2: LPS_UPD(256, 64, 8, 1); break;
+    default:  // best of the first B200 sweep (profiles/r01_update_variants.md)
     case 3: LPS_UPD(128, 32, 8, 2); break;
     case 4: LPS_UPD(512, 32, 4, 1); break;
     case 5: LPS_UPD(256, 32, 8, 2); break;
@@ -202,6 +202,7 @@ void lps_default_options(lps_options* o) {
   o->epsilon = 1e-9;
   o->inf = 1e50;
   o->device = -1;
+  o->update_variant = -1;
 }
 
 const char* lps_status_string(int s) {

@@ -12,7 +12,7 @@ class LPStandardForm:
     def __init__(self, A, b, c, m: int, n: int, maximize: bool,
                  variables: Optional[Dict[int, str]] = None,
                  coefficients: Optional[Dict[str, int]] = None):
-        self.A = np.ascontiguousarray(np.array(A, dtype=np.float64).reshape(m, n)) if m * n else np.zeros((m, n))
+        self.A = np.ascontiguousarray(np.asarray(A, dtype=np.float64).reshape(m, n)) if m * n else np.zeros((m, n))
         self.b = np.array([float(x) for x in b], dtype=np.float64) if not isinstance(b, np.ndarray) else b.astype(np.float64)
         self.c = np.array([float(x) for x in c], dtype=np.float64) if not isinstance(c, np.ndarray) else c.astype(np.float64)
         self.m = m

@@ -48,12 +48,12 @@ class LPState:
         rc = self._lib.lps_create(byref(self._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + self._lib.lps_status_string(rc).decode())
-        A = np.ascontiguousarray(np.array(A, dtype=np.float64).reshape(m, n)) if m * n else np.zeros((m, max(n, 1)))
-        b = np.ascontiguousarray(np.array(b, dtype=np.float64).reshape(m))
+        A = np.ascontiguousarray(np.asarray(A, dtype=np.float64).reshape(m, n)) if m * n else np.zeros((m, max(n, 1)))
+        b = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(m))
         if _aux:
             self._ck(self._lib.lps_load_aux(self._h, m, n, _dp(A), A.strides[0] // 8 if m else n, _dp(b)), "lps_load_aux")
         else:
-            c = np.ascontiguousarray(np.array(c, dtype=np.float64).reshape(n))
+            c = np.ascontiguousarray(np.asarray(c, dtype=np.float64).reshape(n))
             self._ck(self._lib.lps_load(self._h, m, n, _dp(A), A.strides[0] // 8 if m else max(n, 1), _dp(b), _dp(c),
                                         float(v)), "lps_load")
 
@@ -74,7 +74,7 @@ class LPState:
         opts.inf = kw.get("inf", cls.DEF_INF)
         opts.device = kw.get("device", -1)
         opts.time_kernels = int(kw.get("time_kernels", False))
-        opts.update_variant = int(kw.get("update_variant", 0))
+        opts.update_variant = int(kw.get("update_variant", -1))
         rc = st._lib.lps_create(byref(st._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + st._lib.lps_status_string(rc).decode())

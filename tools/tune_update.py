@@ -1,7 +1,10 @@
 """Time the tableau-update kernel variants on a synthetic dense LP (GPU box only).
 usage: python tools/tune_update.py [m n pivots] [variants...]"""
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import linear_programming_solver_b200 as L
 
