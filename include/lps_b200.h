@@ -142,6 +142,26 @@ int lps_drop_column(lps_handle h, int j);
 /* restoreInitialLP — LPSolver.java:213-233: c <- 0, v <- 0, then apply ops in order */
 int lps_rebuild_objective(lps_handle h, const lps_objective_op *ops, int nops);
 
+/* ---- row sharding across the GPUs of one NVSwitch box -------------------------
+ * Rank k of `world` (<= 8) owns rows [k*m/world, (k+1)*m/world) of (A | b) — the block split of
+ * LPState.pivotConcurrently (LPState.java:222-223) — plus a replica of the objective row.  One
+ * handle per GPU; one host process per GPU (multi-process, CUDA IPC) or one process driving
+ * several handles (peer pointers).  Per pivot the ranks exchange their ratio-test candidates
+ * and the owner of the leaving row broadcasts the scaled pivot row by direct stores into peer
+ * memory over NVLink, inside the kernels; lps_run must then be called on every rank with the
+ * same max_pivots.  Field reads return the LOCAL rows; positions and the pivot log are global. */
+int lps_shard_generate_dense(lps_handle h, int m_total, int n, int rank, int world, uint64_t seed,
+                             int pos_permille);
+int lps_shard_load(lps_handle h, int m_total, int n, int rank, int world, const double *A_local,
+                   int64_t lda, const double *b_local, const double *c, double v);
+int lps_shard_info(lps_handle h, int *rank, int *world, int *m_total, int *row0, int *row1);
+/* exchange block: export as a 64-byte CUDA IPC handle (multi-process) or a raw device pointer
+ * (same process, peer access enabled by the caller), then attach all ranks' blocks in rank order */
+int lps_shard_export(lps_handle h, void *handle64);
+int lps_shard_comm_ptr(lps_handle h, void **ptr);
+int lps_shard_attach_ipc(lps_handle h, const void *handles);
+int lps_shard_attach_ptrs(lps_handle h, void *const *comm_ptrs);
+
 /* introspection */
 int lps_device_info(lps_handle h, int *sm_count, int64_t *hbm_bytes, int *cc_major, int *cc_minor);
 int lps_tableau_bytes(lps_handle h, int64_t *bytes);     /* 8*(m+1)*pitch */

@@ -79,6 +79,13 @@ SIGNATURES = {
     "lps_device_info": (c_int, [c_void_p, _ip, POINTER(c_int64), _ip, _ip]),
     "lps_tableau_bytes": (c_int, [c_void_p, POINTER(c_int64)]),
     "lps_algorithmic_bytes_per_pivot": (c_int, [c_void_p, POINTER(c_int64)]),
+    "lps_shard_generate_dense": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_uint64, c_int]),
+    "lps_shard_load": (c_int, [c_void_p, c_int, c_int, c_int, c_int, _dp, c_int64, _dp, _dp, c_double]),
+    "lps_shard_info": (c_int, [c_void_p, _ip, _ip, _ip, _ip, _ip]),
+    "lps_shard_export": (c_int, [c_void_p, c_void_p]),
+    "lps_shard_comm_ptr": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "lps_shard_attach_ipc": (c_int, [c_void_p, c_void_p]),
+    "lps_shard_attach_ptrs": (c_int, [c_void_p, POINTER(c_void_p)]),
     "lpsolver_solve": (c_int, [POINTER(LpsOptions), c_int, c_int, _dp, c_int64, _dp, _dp, c_int, c_int,
                                c_int64, POINTER(LpsolverResult), _dp, _ip, c_int64, _ip, c_int64,
                                POINTER(c_void_p)]),

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "lps_kernels.cuh"
+#include "lps_sharded.cuh"
 
 using namespace lps;
 
@@ -34,8 +35,10 @@ struct lps_handle_s {
   size_t pos_cap = 0;
   int2* plog = nullptr;
   long long log_cap = 1ll << 22;
-  Ctl* ctl = nullptr;
-  Ctl* h_ctl = nullptr;  // pinned
+  CtlS* ctls = nullptr;   // device control block (single-GPU kernels use its `base`)
+  Ctl* ctl = nullptr;     // == &ctls->base
+  CtlS* h_ctls = nullptr; // pinned host copy
+  Ctl* h_ctl = nullptr;   // == &h_ctls->base
   Cand* partials = nullptr;
   ObjOp* d_ops = nullptr;
   size_t ops_cap = 0;
@@ -45,6 +48,15 @@ struct lps_handle_s {
   // colbuf[npivots&1] holds this column (or -1)
   int col_holds = -1;
   long long total_pivots = 0;
+
+  // row-sharded mode (lps_shard_*): this handle holds rows [row0,row1) of an m_total-row LP
+  bool sharded = false;
+  int rank = 0, world = 1, m_total = 0, row0 = 0, row1 = 0;
+  CommBlock* comm = nullptr;
+  size_t comm_bytes = 0;
+  Peers peers{};
+  bool attached = false;
+  std::vector<void*> ipc_opened;
 
   std::vector<cudaEvent_t> ev;  // time_kernels event pool
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -120,7 +132,7 @@ int ensure_buffers(lps_handle h, int m, int n_cols /* n incl. any aux column */)
 }
 
 int reset_state(lps_handle h) {
-  CK(cudaMemsetAsync(h->ctl, 0, sizeof(Ctl), h->stream));
+  CK(cudaMemsetAsync(h->ctls, 0, sizeof(CtlS), h->stream));
   int tot = h->m + h->n;
   k_iota<<<cdiv(tot, 256), 256, 0, h->stream>>>(h->pos2var, tot);
   CK(cudaGetLastError());
@@ -132,7 +144,7 @@ int reset_state(lps_handle h) {
 }
 
 int sync_ctl(lps_handle h) {
-  CK(cudaMemcpyAsync(h->h_ctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_ctls, h->ctls, sizeof(CtlS), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return LPS_OK;
 }
@@ -190,6 +202,89 @@ int prepare_next(lps_handle h) {
   return LPS_OK;
 }
 
+
+// ---- row-sharded mode ---------------------------------------------------------------------
+int ensure_comm(lps_handle h) {
+  size_t need = sizeof(CommBlock) + 2 * (size_t)h->ld * sizeof(double);
+  if (need > h->comm_bytes) {
+    if (h->attached) return fail(h, LPS_ERR_STATE, "shard: tableau grew after peers were attached");
+    if (h->comm) cudaFree(h->comm);
+    cudaError_t ce = cudaMalloc(&h->comm, need);
+    if (ce != cudaSuccess) return fail(h, LPS_ERR_NOMEM, "cudaMalloc(comm block)", ce);
+    h->comm_bytes = need;
+  }
+  CK(cudaMemsetAsync(h->comm, 0, h->comm_bytes, h->stream));
+  // until peers are attached the rank talks to itself (world == 1 works out of the box)
+  for (int k = 0; k < kMaxRanks; k++) {
+    h->peers.blk[k] = h->comm;
+    h->peers.rowbuf[k] = reinterpret_cast<double*>(reinterpret_cast<char*>(h->comm) + sizeof(CommBlock));
+  }
+  return LPS_OK;
+}
+
+int shard_setup(lps_handle h, int m_total, int n, int rank, int world) {
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || m_total < 0 || n < 0)
+    return fail(h, LPS_ERR_INVALID, "shard: bad rank/world/dimensions");
+  if ((long long)n + 1 > (long long)kMaxChunks * kChunk) return fail(h, LPS_ERR_INVALID, "shard: too many columns");
+  h->sharded = true;
+  h->rank = rank;
+  h->world = world;
+  h->m_total = m_total;
+  h->row0 = (int)(((long long)rank * m_total) / world);        // LPState.java:222
+  h->row1 = (int)(((long long)(rank + 1) * m_total) / world);  // LPState.java:223
+  int rc = ensure_buffers(h, h->row1 - h->row0, n);
+  if (rc) return rc;
+  // positions are global: n + m_total entries
+  size_t pneed = (size_t)m_total + n + 16;
+  if (pneed > h->pos_cap) {
+    if (h->pos2var) cudaFree(h->pos2var);
+    cudaError_t ce = cudaMalloc(&h->pos2var, pneed * sizeof(int));
+    if (ce != cudaSuccess) return fail(h, LPS_ERR_NOMEM, "cudaMalloc(positions)", ce);
+    h->pos_cap = pneed;
+  }
+  return ensure_comm(h);
+}
+
+int shard_reset_state(lps_handle h) {
+  CK(cudaMemsetAsync(h->ctls, 0, sizeof(CtlS), h->stream));
+  int tot = h->m_total + h->n;
+  k_iota<<<cdiv(tot, 256), 256, 0, h->stream>>>(h->pos2var, tot);
+  CK(cudaGetLastError());
+  h->next_valid = false;
+  h->col_holds = -1;
+  h->total_pivots = 0;
+  h->loaded = true;
+  return LPS_OK;
+}
+
+int shard_prepare_next(lps_handle h) {
+  if (h->next_valid) return LPS_OK;
+  ks_begin_run<<<1, 1, 0, h->stream>>>(h->ctls, -1, 1);
+  ks_first_positive<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->ctls, h->T + (long long)h->m * h->ld, h->n,
+                                                           h->opt.epsilon);
+  ks_extract<<<cdiv(h->m + 1, 256), 256, 0, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->n, -1, h->col0,
+                                                        h->col1, h->bcol);
+  CK(cudaGetLastError());
+  h->next_valid = true;
+  return LPS_OK;
+}
+
+void shard_launch_pivot(lps_handle h, bool cap_step, cudaEvent_t e0, cudaEvent_t e1) {
+  ks_ratio<<<ratio_grid(h), kRatioThreads, 0, h->stream>>>(h->ctls, h->col0, h->col1, h->bcol, h->m, h->row0,
+                                                          h->opt.epsilon, h->opt.inf, h->partials, h->peers,
+                                                          h->rank, h->world);
+  ks_scale_row<<<cdiv(h->ld, kChunk), kChunk, 0, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->n, h->row0, h->row1,
+                                                             h->col0, h->col1, h->opt.epsilon, h->opt.inf,
+                                                             h->peers, h->rank, h->world, h->plog, h->log_cap,
+                                                             h->pos2var);
+  if (cap_step) return;
+  if (e0) cudaEventRecord(e0, h->stream);
+  dim3 grid(cdiv(h->ld, 4ll * 128), cdiv(h->m + 1, 32));
+  ks_update<128, 32, 8, 2><<<grid, 128, 0, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->n, h->row0, h->row1,
+                                                       h->peers.rowbuf[h->rank], h->col0, h->col1, h->bcol);
+  if (e1) cudaEventRecord(e1, h->stream);
+}
+
 }  // namespace
 
 extern "C" {
@@ -242,8 +337,12 @@ int lps_create(lps_handle* out, const lps_options* opts) {
       h->own_stream = true;
     }
   }
-  if (ce == cudaSuccess) ce = cudaMalloc(&h->ctl, sizeof(Ctl));
-  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_ctl, sizeof(Ctl));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->ctls, sizeof(CtlS));
+  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_ctls, sizeof(CtlS));
+  if (ce == cudaSuccess) {
+    h->ctl = &h->ctls->base;
+    h->h_ctl = &h->h_ctls->base;
+  }
   if (ce == cudaSuccess) ce = cudaMalloc(&h->partials, 4096 * sizeof(Cand));
   if (ce == cudaSuccess) ce = cudaMalloc(&h->plog, (size_t)h->log_cap * sizeof(int2));
   if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev_begin);
@@ -264,8 +363,10 @@ int lps_destroy(lps_handle h) {
   for (double* p : {h->col0, h->col1, h->bcol, h->scratch, h->rowbuf}) if (p) cudaFree(p);
   if (h->pos2var) cudaFree(h->pos2var);
   if (h->plog) cudaFree(h->plog);
-  if (h->ctl) cudaFree(h->ctl);
-  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  if (h->comm) cudaFree(h->comm);
+  if (h->ctls) cudaFree(h->ctls);
+  if (h->h_ctls) cudaFreeHost(h->h_ctls);
   if (h->partials) cudaFree(h->partials);
   if (h->d_ops) cudaFree(h->d_ops);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -341,6 +442,7 @@ int lps_generate_dense(lps_handle h, int m, int n, uint64_t seed, int pos_permil
 
 int lps_get_entering(lps_handle h, int* e) {
   if (!h || !e) return LPS_ERR_INVALID;
+  if (h->sharded) return fail(h, LPS_ERR_STATE, "not available on a row shard (use lps_run)");
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
   CK(cudaSetDevice(h->dev));
   int rc = prepare_next(h);
@@ -353,6 +455,7 @@ int lps_get_entering(lps_handle h, int* e) {
 
 int lps_get_leaving(lps_handle h, int e, int* l) {
   if (!h || !l) return LPS_ERR_INVALID;
+  if (h->sharded) return fail(h, LPS_ERR_STATE, "not available on a row shard (use lps_run)");
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
   if (e < 0 || e >= h->n) return fail(h, LPS_ERR_INVALID, "getLeaving: entering out of range");
   CK(cudaSetDevice(h->dev));
@@ -371,6 +474,7 @@ int lps_get_leaving(lps_handle h, int e, int* l) {
 
 int lps_pivot(lps_handle h, int e, int l) {
   if (!h) return LPS_ERR_INVALID;
+  if (h->sharded) return fail(h, LPS_ERR_STATE, "not available on a row shard (use lps_run)");
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
   if (e < 0 || e >= h->n || l < 0 || l >= h->m)
     return fail(h, LPS_ERR_INVALID, "pivot: index out of range");
@@ -403,10 +507,11 @@ int lps_run(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   const long long start_pivots = h->total_pivots;
   long long launches = 0;
   CK(cudaEventRecord(h->ev_begin, h->stream));
-  int rc = prepare_next(h);
+  int rc = h->sharded ? shard_prepare_next(h) : prepare_next(h);
   if (rc) return rc;
   launches += 3;
-  k_begin_run<<<1, 1, 0, h->stream>>>(h->ctl, max_pivots, 0);
+  if (h->sharded) ks_begin_run<<<1, 1, 0, h->stream>>>(h->ctls, max_pivots, 0);
+  else k_begin_run<<<1, 1, 0, h->stream>>>(h->ctl, max_pivots, 0);
   launches++;
 
   // batch size: about 30 ms of device work per host check, from the tableau's size
@@ -429,10 +534,19 @@ int lps_run(lps_handle h, int64_t max_pivots, lps_run_result* res) {
     // one extra ratio step past the cap is what turns "cap reached" into a verdict
     long long todo = (remaining < 0) ? batch : std::min(batch, remaining + 1);
     for (long long k = 0; k < todo; k++) {
+      const bool cap_step = remaining >= 0 && k == remaining;  // the step that only reports PIVOT_CAP
+      if (h->sharded) {
+        shard_launch_pivot(h, cap_step, timed ? h->ev[2 * k] : nullptr, timed ? h->ev[2 * k + 1] : nullptr);
+        launches += cap_step ? 2 : 3;
+        if (cap_step) break;
+        continue;
+      }
       launch_ratio(h, 0);
+      launches++;
+      if (cap_step) break;
       launch_scale_update(h, timed ? h->ev[2 * k] : nullptr, timed ? h->ev[2 * k + 1] : nullptr);
+      launches += 2;
     }
-    launches += 3 * todo;
     CK(cudaGetLastError());
     rc = sync_ctl(h);
     if (rc) return rc;
@@ -448,6 +562,7 @@ int lps_run(lps_handle h, int64_t max_pivots, lps_run_result* res) {
     if (remaining >= 0) remaining -= done_now;
     if (h->h_ctl->status != kRunning) break;
   }
+  if (h->h_ctl->status == kCommTimeout) return fail(h, LPS_ERR_COMM, "shard: timed out waiting for a peer rank");
   CK(cudaEventRecord(h->ev_end, h->stream));
   CK(cudaEventSynchronize(h->ev_end));
   // after a terminal verdict the staged (e_next, column) pair is still the one the verdict was
@@ -551,14 +666,15 @@ int lps_read_positions(lps_handle h, int* pos2var) {
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
   CK(cudaSetDevice(h->dev));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(pos2var, h->pos2var, (size_t)(h->m + h->n) * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pos2var, h->pos2var, (size_t)((h->sharded ? h->m_total : h->m) + h->n) * sizeof(int),
+                cudaMemcpyDeviceToHost));
   return LPS_OK;
 }
 
 int lps_position_of(lps_handle h, int var, int* pos) {
   if (!h || !pos) return LPS_ERR_INVALID;
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
-  std::vector<int> p((size_t)h->m + h->n);
+  std::vector<int> p((size_t)(h->sharded ? h->m_total : h->m) + h->n);
   int rc = lps_read_positions(h, p.data());
   if (rc) return rc;
   *pos = -1;
@@ -590,6 +706,7 @@ int lps_read_pivot_log(lps_handle h, int* pairs, int64_t cap_pairs, int64_t* cou
 int lps_read_primal(lps_handle h, int nvars, double* x) {
   if (!h || !x || nvars < 0) return LPS_ERR_INVALID;
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  if (h->sharded) return fail(h, LPS_ERR_STATE, "read_primal: gather b from the shards first");
   std::vector<int> p((size_t)h->m + h->n);
   std::vector<double> b((size_t)h->m);
   int rc = lps_read_positions(h, p.data());
@@ -606,6 +723,7 @@ int lps_read_primal(lps_handle h, int nvars, double* x) {
 
 int lps_first_nonzero_in_row(lps_handle h, int row, int* j) {
   if (!h || !j) return LPS_ERR_INVALID;
+  if (h->sharded) return fail(h, LPS_ERR_STATE, "not available on a row shard (use lps_run)");
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
   if (row < 0 || row >= h->m) return fail(h, LPS_ERR_INVALID, "first_nonzero_in_row: row out of range");
   CK(cudaSetDevice(h->dev));
@@ -622,6 +740,7 @@ int lps_first_nonzero_in_row(lps_handle h, int row, int* j) {
 
 int lps_drop_column(lps_handle h, int j) {
   if (!h) return LPS_ERR_INVALID;
+  if (h->sharded) return fail(h, LPS_ERR_STATE, "not available on a row shard (use lps_run)");
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
   if (j < 0 || j >= h->n) return fail(h, LPS_ERR_INVALID, "drop_column: column out of range");
   CK(cudaSetDevice(h->dev));
@@ -687,6 +806,129 @@ int lps_algorithmic_bytes_per_pivot(lps_handle h, int64_t* bytes) {
   if (!h || !bytes || !h->loaded) return LPS_ERR_STATE;
   *bytes = 16ll * (h->m + 1) * (h->n + 1);
   return LPS_OK;
+}
+
+// ---- row-sharded API ------------------------------------------------------------------------
+int lps_shard_generate_dense(lps_handle h, int m_total, int n, int rank, int world, uint64_t seed,
+                             int pos_permille) {
+  if (!h || m_total <= 0 || n <= 0) return fail(h, LPS_ERR_INVALID, "lps_shard_generate_dense: bad dimensions");
+  CK(cudaSetDevice(h->dev));
+  int rc = shard_setup(h, m_total, n, rank, world);
+  if (rc) return rc;
+  dim3 grid(std::min(cdiv(h->ld, 256), 64), std::min(h->m + 1, 65535));
+  ks_generate_dense<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m_total, n, h->row0, h->row1, seed, pos_permille);
+  CK(cudaGetLastError());
+  rc = shard_reset_state(h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return LPS_OK;
+}
+
+int lps_shard_load(lps_handle h, int m_total, int n, int rank, int world, const double* A_local,
+                   int64_t lda, const double* b_local, const double* c, double v) {
+  if (!h) return LPS_ERR_INVALID;
+  if (lda < n || (n > 0 && !c)) return fail(h, LPS_ERR_INVALID, "lps_shard_load: bad arguments");
+  CK(cudaSetDevice(h->dev));
+  int rc = shard_setup(h, m_total, n, rank, world);
+  if (rc) return rc;
+  const int m = h->m;
+  const long long ld = h->ld;
+  if (m > 0 && (!A_local || !b_local)) return fail(h, LPS_ERR_INVALID, "lps_shard_load: null buffer");
+  CK(cudaMemsetAsync(h->T, 0, (size_t)(m + 1) * ld * sizeof(double), h->stream));
+  if (m > 0 && n > 0)
+    CK(cudaMemcpy2DAsync(h->T, ld * sizeof(double), A_local, (size_t)lda * sizeof(double),
+                         (size_t)n * sizeof(double), m, cudaMemcpyHostToDevice, h->stream));
+  if (m > 0) {
+    CK(cudaMemcpyAsync(h->scratch, b_local, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_set_column<<<cdiv(m, 256), 256, 0, h->stream>>>(h->T, ld, m, n, h->scratch, 0.0, 0);
+  }
+  if (n > 0)
+    CK(cudaMemcpyAsync(h->T + (long long)m * ld, c, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const double negv = -v;
+  CK(cudaMemcpyAsync(h->T + (long long)m * ld + n, &negv, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaGetLastError());
+  rc = shard_reset_state(h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return LPS_OK;
+}
+
+int lps_shard_info(lps_handle h, int* rank, int* world, int* m_total, int* row0, int* row1) {
+  if (!h || !h->sharded) return LPS_ERR_STATE;
+  if (rank) *rank = h->rank;
+  if (world) *world = h->world;
+  if (m_total) *m_total = h->m_total;
+  if (row0) *row0 = h->row0;
+  if (row1) *row1 = h->row1;
+  return LPS_OK;
+}
+
+int lps_shard_export(lps_handle h, void* handle64) {
+  if (!h || !handle64) return LPS_ERR_INVALID;
+  if (!h->sharded || !h->comm) return fail(h, LPS_ERR_STATE, "shard: nothing loaded");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  CK(cudaSetDevice(h->dev));
+  cudaIpcMemHandle_t ih;
+  CK(cudaIpcGetMemHandle(&ih, h->comm));
+  std::memcpy(handle64, &ih, 64);
+  return LPS_OK;
+}
+
+int lps_shard_comm_ptr(lps_handle h, void** p) {
+  if (!h || !p) return LPS_ERR_INVALID;
+  if (!h->sharded || !h->comm) return fail(h, LPS_ERR_STATE, "shard: nothing loaded");
+  *p = h->comm;
+  return LPS_OK;
+}
+
+static int attach_common(lps_handle h, void* const* blocks) {
+  for (int k = 0; k < h->world; k++) {
+    CommBlock* b = (k == h->rank) ? h->comm : reinterpret_cast<CommBlock*>(blocks[k]);
+    if (!b) return fail(h, LPS_ERR_INVALID, "shard attach: null peer block");
+    h->peers.blk[k] = b;
+    h->peers.rowbuf[k] = reinterpret_cast<double*>(reinterpret_cast<char*>(b) + sizeof(CommBlock));
+  }
+  h->attached = true;
+  return LPS_OK;
+}
+
+int lps_shard_attach_ptrs(lps_handle h, void* const* comm_ptrs) {
+  if (!h || !comm_ptrs) return LPS_ERR_INVALID;
+  if (!h->sharded || !h->comm) return fail(h, LPS_ERR_STATE, "shard: nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  // same-process peers: make their memory addressable from this device
+  for (int k = 0; k < h->world; k++) {
+    if (k == h->rank || !comm_ptrs[k]) continue;
+    cudaPointerAttributes at;
+    CK(cudaPointerGetAttributes(&at, comm_ptrs[k]));
+    if (at.device != h->dev) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, h->dev, at.device));
+      if (!can) return fail(h, LPS_ERR_COMM, "shard attach: no peer access between the two GPUs");
+      cudaError_t ce = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) return fail(h, LPS_ERR_COMM, "cudaDeviceEnablePeerAccess", ce);
+      cudaGetLastError();
+    }
+  }
+  return attach_common(h, comm_ptrs);
+}
+
+int lps_shard_attach_ipc(lps_handle h, const void* handles /* world x 64 bytes, rank order */) {
+  if (!h || !handles) return LPS_ERR_INVALID;
+  if (!h->sharded || !h->comm) return fail(h, LPS_ERR_STATE, "shard: nothing loaded");
+  CK(cudaSetDevice(h->dev));
+  void* blocks[kMaxRanks] = {nullptr};
+  for (int k = 0; k < h->world; k++) {
+    if (k == h->rank) continue;
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, static_cast<const char*>(handles) + 64 * k, 64);
+    void* p = nullptr;
+    cudaError_t ce = cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess);
+    if (ce != cudaSuccess) return fail(h, LPS_ERR_COMM, "cudaIpcOpenMemHandle", ce);
+    h->ipc_opened.push_back(p);
+    blocks[k] = p;
+  }
+  return attach_common(h, blocks);
 }
 
 }  // extern "C"
