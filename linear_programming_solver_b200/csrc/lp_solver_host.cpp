@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 
+static_assert(sizeof(lpsolver_result) == 256, "lpsolver_result layout");
+
 namespace lpsolver {
 
 // ---- LPState -------------------------------------------------------------------------------

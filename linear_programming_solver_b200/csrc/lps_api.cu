@@ -16,6 +16,11 @@
 
 using namespace lps;
 
+// layouts the ctypes / JNI bindings rely on (tests/test_abi.py checks the Python side)
+static_assert(sizeof(lps_options) == 64, "lps_options layout");
+static_assert(sizeof(lps_run_result) == 64, "lps_run_result layout");
+static_assert(sizeof(lps_objective_op) == 16, "lps_objective_op layout");
+
 struct lps_handle_s {
   lps_options opt;
   int dev = 0;
