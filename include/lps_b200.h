@@ -55,8 +55,10 @@ typedef struct {
   int device;           /* CUDA device ordinal, -1 = current device */
   int time_kernels;     /* != 0: bracket every tableau-update launch with CUDA events */
   void *stream;         /* cudaStream_t to run on, NULL = the handle creates its own */
-  int update_variant;   /* tableau-update kernel: 0 = default, >0 selects an alternative (tuning) */
-  int reserved[7];
+  int update_variant;   /* tableau-update kernel: -1 = default, >= 0 selects an alternative (tuning) */
+  int loop_mode;        /* lps_run: 0 = auto, 1 = three kernels per pivot, 2 = one persistent
+                           cooperative kernel for the whole loop (grid barriers between phases) */
+  int reserved[6];
 } lps_options;
 
 typedef struct {

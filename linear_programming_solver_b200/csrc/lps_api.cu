@@ -13,6 +13,7 @@
 
 #include "lps_kernels.cuh"
 #include "lps_sharded.cuh"
+#include "lps_loop.cuh"
 
 using namespace lps;
 
@@ -50,6 +51,10 @@ struct lps_handle_s {
 
   // device-side (e_next, colbuf[npivots&1], bcol) are consistent with the tableau
   bool next_valid = false;
+  // where the staged entering index lives: false = Ctl::e_next (three-kernel single-GPU path),
+  // true = CtlS::e_nx[(npivots+1)&1] (sharded kernels and the persistent loop)
+  bool next_in_nx = false;
+  int loop_grid = 0;  // co-resident CTAs of k_loop (0 = not queried yet)
   // colbuf[npivots&1] holds this column (or -1)
   int col_holds = -1;
   long long total_pivots = 0;
@@ -203,6 +208,7 @@ int prepare_next(lps_handle h) {
                                                        h->col1, h->bcol);
   CK(cudaGetLastError());
   h->next_valid = true;
+  h->next_in_nx = false;
   h->col_holds = -2;  // "whatever e_next is"
   return LPS_OK;
 }
@@ -271,6 +277,7 @@ int shard_prepare_next(lps_handle h) {
                                                         h->col1, h->bcol);
   CK(cudaGetLastError());
   h->next_valid = true;
+  h->next_in_nx = true;
   return LPS_OK;
 }
 
@@ -288,6 +295,67 @@ void shard_launch_pivot(lps_handle h, bool cap_step, cudaEvent_t e0, cudaEvent_t
   ks_update<128, 32, 8, 2><<<grid, 128, 0, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->n, h->row0, h->row1,
                                                        h->peers.rowbuf[h->rank], h->col0, h->col1, h->bcol);
   if (e1) cudaEventRecord(e1, h->stream);
+}
+
+
+// ---- persistent loop ------------------------------------------------------------------------
+__global__ void k_convert_next(CtlS* ctl, int to_nx) {
+  const int slot = (int)((ctl->base.npivots + 1) & 1);
+  if (to_nx) ctl->e_nx[slot] = ctl->base.e_next;
+  else ctl->base.e_next = ctl->e_nx[slot];
+}
+
+int ensure_next_fmt(lps_handle h, bool want_nx) {
+  if (!h->next_valid || h->next_in_nx == want_nx) return LPS_OK;
+  k_convert_next<<<1, 1, 0, h->stream>>>(h->ctls, want_nx ? 1 : 0);
+  CK(cudaGetLastError());
+  h->next_in_nx = want_nx;
+  return LPS_OK;
+}
+
+bool use_persistent(lps_handle h) {
+  if (h->opt.loop_mode == 1) return false;
+  if (h->opt.loop_mode == 2) return true;
+  return false;  // auto
+}
+
+int launch_loop(lps_handle h) {
+  if (h->loop_grid == 0) {
+    int coop = 0, nb = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->dev));
+    if (!coop) return fail(h, LPS_ERR_STATE, "device does not support cooperative launch");
+    if (h->sharded) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_loop<true>, kLoopThreads, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_loop<false>, kLoopThreads, 0));
+    if (nb < 1) return fail(h, LPS_ERR_STATE, "k_loop does not fit on an SM");
+    h->loop_grid = nb * h->sm_count;
+  }
+  LoopArgs la;
+  la.ctl = h->ctls;
+  la.T = h->T;
+  la.ld = h->ld;
+  la.mloc = h->m;
+  la.n = h->n;
+  la.row0 = h->sharded ? h->row0 : 0;
+  la.row1 = h->sharded ? h->row1 : h->m;
+  la.col0 = h->col0;
+  la.col1 = h->col1;
+  la.bcol = h->bcol;
+  la.rowbuf = h->rowbuf;
+  la.partials = h->partials;
+  la.plog = h->plog;
+  la.log_cap = h->log_cap;
+  la.pos2var = h->pos2var;
+  la.eps = h->opt.epsilon;
+  la.inf = h->opt.inf;
+  la.peers = h->peers;
+  la.rank = h->rank;
+  la.world = h->world;
+  void* args[] = {&la};
+  if (h->sharded)
+    CK(cudaLaunchCooperativeKernel((void*)k_loop<true>, dim3(h->loop_grid), dim3(kLoopThreads), args, 0, h->stream));
+  else
+    CK(cudaLaunchCooperativeKernel((void*)k_loop<false>, dim3(h->loop_grid), dim3(kLoopThreads), args, 0, h->stream));
+  return LPS_OK;
 }
 
 }  // namespace
@@ -450,7 +518,7 @@ int lps_get_entering(lps_handle h, int* e) {
   if (h->sharded) return fail(h, LPS_ERR_STATE, "not available on a row shard (use lps_run)");
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
   CK(cudaSetDevice(h->dev));
-  int rc = prepare_next(h);
+  int rc = h->next_valid ? ensure_next_fmt(h, false) : prepare_next(h);
   if (rc) return rc;
   rc = sync_ctl(h);
   if (rc) return rc;
@@ -501,6 +569,7 @@ int lps_pivot(lps_handle h, int e, int l) {
   }
   h->total_pivots = h->h_ctl->npivots;
   h->next_valid = true;  // k_scale_row/k_update staged the next entering column
+  h->next_in_nx = false;
   h->col_holds = -2;
   return LPS_OK;
 }
@@ -512,9 +581,44 @@ int lps_run(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   const long long start_pivots = h->total_pivots;
   long long launches = 0;
   CK(cudaEventRecord(h->ev_begin, h->stream));
-  int rc = h->sharded ? shard_prepare_next(h) : prepare_next(h);
+  const bool persistent = use_persistent(h);
+  int rc = LPS_OK;
+  if (h->next_valid) rc = ensure_next_fmt(h, persistent || h->sharded);
+  else rc = (h->sharded || persistent) ? shard_prepare_next(h) : prepare_next(h);
   if (rc) return rc;
   launches += 3;
+  if (persistent) {
+    ks_begin_run<<<1, 1, 0, h->stream>>>(h->ctls, max_pivots, 0);
+    rc = launch_loop(h);
+    if (rc) return rc;
+    launches += 2;
+    rc = sync_ctl(h);
+    if (rc) return rc;
+    if (h->h_ctl->status == kCommTimeout) return fail(h, LPS_ERR_COMM, "shard: timed out waiting for a peer rank");
+    CK(cudaEventRecord(h->ev_end, h->stream));
+    CK(cudaEventSynchronize(h->ev_end));
+    const long long done = h->h_ctl->npivots - h->total_pivots;
+    h->total_pivots = h->h_ctl->npivots;
+    h->next_valid = (h->h_ctl->status == kPivotCap);
+    h->next_in_nx = true;
+    h->col_holds = h->next_valid ? -2 : -1;
+    if (res) {
+      std::memset(res, 0, sizeof(*res));
+      res->verdict = h->h_ctl->status;
+      res->last_entering = h->h_ctl->e_cur;
+      res->last_leaving = h->h_ctl->l_cur;
+      res->npivots = done;
+      res->total_pivots = h->total_pivots;
+      double corner = 0.0;
+      CK(cudaMemcpy(&corner, h->T + (long long)h->m * h->ld + h->n, sizeof(double), cudaMemcpyDeviceToHost));
+      res->v = 0.0 - corner;
+      cudaEventElapsedTime(&res->device_ms, h->ev_begin, h->ev_end);
+      res->update_ms = (float)(h->h_ctls->upd_ns * 1e-6);
+      res->update_launches = done;
+      res->kernel_launches = launches;
+    }
+    return LPS_OK;
+  }
   if (h->sharded) ks_begin_run<<<1, 1, 0, h->stream>>>(h->ctls, max_pivots, 0);
   else k_begin_run<<<1, 1, 0, h->stream>>>(h->ctl, max_pivots, 0);
   launches++;
@@ -573,6 +677,7 @@ int lps_run(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   // after a terminal verdict the staged (e_next, column) pair is still the one the verdict was
   // taken on, so a later call may continue from it (e.g. after PIVOT_CAP)
   h->next_valid = (h->h_ctl->status == kPivotCap);
+  h->next_in_nx = h->sharded;
   h->col_holds = h->next_valid ? -2 : -1;
   if (res) {
     std::memset(res, 0, sizeof(*res));

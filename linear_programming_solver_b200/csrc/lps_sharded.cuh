@@ -26,7 +26,7 @@ namespace lps {
 
 constexpr int kMaxRanks = 8;
 constexpr int kChunk = 256;           // columns per ks_scale_row CTA == flag granularity
-constexpr int kMaxChunks = 2048;      // supports n+1 <= 524288 columns
+constexpr int kMaxChunks = 4096;      // flag slots per parity (n+1 <= 524288 at 128-column chunks)
 constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 enum : int { kCommTimeout = 5 };
@@ -93,6 +93,10 @@ struct CtlS {
   int e_nx[2];
   int owner;          // rank that owns the leaving row of the pivot in flight
   unsigned int ticket2;
+  int abort;          // persistent loop: a CTA gave up (peer timeout); everyone leaves
+  int pad_;
+  unsigned long long bar;     // persistent loop: grid-barrier counter
+  unsigned long long upd_ns;  // persistent loop: accumulated phase-C time
 };
 
 __global__ void ks_begin_run(CtlS* ctl, long long max_pivots, int reset_next) {
@@ -100,6 +104,9 @@ __global__ void ks_begin_run(CtlS* ctl, long long max_pivots, int reset_next) {
   ctl->base.pivot_limit = (max_pivots < 0) ? LLONG_MAX : ctl->base.npivots + max_pivots;
   ctl->base.ticket = 0;
   ctl->ticket2 = 0;
+  ctl->abort = 0;
+  ctl->bar = 0;
+  ctl->upd_ns = 0;
   if (reset_next) ctl->e_nx[(ctl->base.npivots + 1) & 1] = kNone;
 }
 

@@ -34,7 +34,7 @@ class LPState:
                  variables: Optional[Dict[int, str]] = None,
                  coefficients: Optional[Dict[str, int]] = None,
                  epsilon: float = DEF_EPSILON, inf: float = DEF_INF, device: int = -1,
-                 time_kernels: bool = False, _handle=None, _aux=False):
+                 time_kernels: bool = False, loop_mode: int = 0, _handle=None, _aux=False):
         self._lib = N.load()
         self._h = c_void_p()
         self._names0 = None
@@ -45,6 +45,7 @@ class LPState:
             return
         opts = N.default_options()
         opts.epsilon, opts.inf, opts.device, opts.time_kernels = epsilon, inf, device, int(time_kernels)
+        opts.loop_mode = int(loop_mode)
         rc = self._lib.lps_create(byref(self._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + self._lib.lps_status_string(rc).decode())
@@ -75,6 +76,7 @@ class LPState:
         opts.device = kw.get("device", -1)
         opts.time_kernels = int(kw.get("time_kernels", False))
         opts.update_variant = int(kw.get("update_variant", -1))
+        opts.loop_mode = int(kw.get("loop_mode", 0))
         rc = st._lib.lps_create(byref(st._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + st._lib.lps_status_string(rc).decode())

@@ -16,7 +16,9 @@ def main():
     variants = [int(x) for x in sys.argv[4:]] or list(range(8))
     out = []
     for var in variants:
-        st = L.LPState.synthetic_dense(m, n, 0, 1000, time_kernels=True, update_variant=var)
+        # variant >= 100 selects the persistent loop kernel
+        kw = dict(loop_mode=2) if var >= 100 else dict(update_variant=var, loop_mode=1)
+        st = L.LPState.synthetic_dense(m, n, 0, 1000, time_kernels=True, **kw)
         st.run(10)  # warm-up
         r = st.run(pivots)
         bytes_pp = st.algorithmic_bytes_per_pivot()
