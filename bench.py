@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--loop-mode", type=int, default=0, help="0 auto, 1 three kernels per pivot, 2 persistent loop")
     return ap.parse_args()
 
 
@@ -191,7 +192,7 @@ def run_ours(args):
                                      measured_peak, ClockSampler)
 
     m, n, P = args.m, args.n, args.pivots_per_step
-    kw = dict(device=local_rank, time_kernels=True)
+    kw = dict(device=local_rank, time_kernels=True, loop_mode=args.loop_mode)
     if args.variant >= 0:
         kw["update_variant"] = args.variant
     st = L.LPState.synthetic_dense(m, n, args.seed, 1000, **kw)

@@ -315,20 +315,32 @@ int ensure_next_fmt(lps_handle h, bool want_nx) {
 
 bool use_persistent(lps_handle h) {
   if (h->opt.loop_mode == 1) return false;
-  if (h->opt.loop_mode == 2) return true;
-  return false;  // auto
+  if (h->opt.loop_mode >= 2) return true;
+  // auto (profiles/r01_loop_modes.md): the persistent loop wins while the launch chain is a
+  // visible share of a pivot; on multi-GB tableaus the hardware CTA scheduler streams ~1.5 %
+  // faster than the in-kernel tile queue
+  const double bytes = 8.0 * (double)(h->m + 1) * (double)h->ld;
+  return bytes <= 2.5e9;
 }
 
-int launch_loop(lps_handle h) {
+template <bool kSharded, int kU, int kB>
+int launch_loop_t(lps_handle h, const LoopArgs& la_in) {
   if (h->loop_grid == 0) {
     int coop = 0, nb = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->dev));
     if (!coop) return fail(h, LPS_ERR_STATE, "device does not support cooperative launch");
-    if (h->sharded) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_loop<true>, kLoopThreads, 0));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_loop<false>, kLoopThreads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_loop<kSharded, kU, kB>, kGroupThreads * kB, 0));
     if (nb < 1) return fail(h, LPS_ERR_STATE, "k_loop does not fit on an SM");
-    h->loop_grid = nb * h->sm_count;
+    h->loop_grid = h->sm_count;  // one CTA per SM
   }
+  LoopArgs la = la_in;
+  void* args[] = {&la};
+  CK(cudaLaunchCooperativeKernel((void*)k_loop<kSharded, kU, kB>, dim3(h->loop_grid), dim3(kGroupThreads * kB), args,
+                                 0, h->stream));
+  return LPS_OK;
+}
+
+int launch_loop(lps_handle h) {
   LoopArgs la;
   la.ctl = h->ctls;
   la.T = h->T;
@@ -350,12 +362,15 @@ int launch_loop(lps_handle h) {
   la.peers = h->peers;
   la.rank = h->rank;
   la.world = h->world;
-  void* args[] = {&la};
-  if (h->sharded)
-    CK(cudaLaunchCooperativeKernel((void*)k_loop<true>, dim3(h->loop_grid), dim3(kLoopThreads), args, 0, h->stream));
-  else
-    CK(cudaLaunchCooperativeKernel((void*)k_loop<false>, dim3(h->loop_grid), dim3(kLoopThreads), args, 0, h->stream));
-  return LPS_OK;
+  const int shape = h->opt.loop_mode;  // 2 = default shape; 3, 4 = tuning alternatives
+  if (h->sharded) {
+    if (shape == 3) return launch_loop_t<true, 8, 2>(h, la);
+    if (shape == 4) return launch_loop_t<true, 4, 4>(h, la);
+    return launch_loop_t<true, 8, 3>(h, la);
+  }
+  if (shape == 3) return launch_loop_t<false, 8, 2>(h, la);
+  if (shape == 4) return launch_loop_t<false, 4, 4>(h, la);
+  return launch_loop_t<false, 8, 3>(h, la);
 }
 
 }  // namespace

@@ -24,9 +24,8 @@
 
 namespace lps {
 
-constexpr int kLoopThreads = 128;
+constexpr int kGroupThreads = 128;   // one tile-streaming group = 4 warps = 512 columns
 constexpr int kLoopRows = 32;
-constexpr int kLoopUnroll = 8;
 constexpr int kLoopChunk = 128;       // phase-B columns per CTA step == sharded flag granularity
 static_assert(kMaxChunks * kLoopChunk >= 524288, "flag slots");
 
@@ -92,12 +91,16 @@ __device__ __forceinline__ bool grid_barrier(CtlS* ctl, unsigned long long& targ
   return s_alive != 0;
 }
 
-template <bool kSharded>
-__global__ void __launch_bounds__(kLoopThreads, 3) k_loop(const LoopArgs a) {
+// One CTA per SM (grid barriers then cost one arrival per SM); the CTA is kGroups independent
+// 128-thread groups for the streaming phase, each claiming its own tiles.
+template <bool kSharded, int kLoopUnroll, int kGroups>
+__global__ void __launch_bounds__(kGroupThreads * kGroups, 1) k_loop(const LoopArgs a) {
+  constexpr int kLoopThreads = kGroupThreads * kGroups;
   __shared__ Cand sh_c[kLoopThreads / 32];
   __shared__ int sh_i[kLoopThreads / 32];
   __shared__ double s_slack, s_p;
-  __shared__ int s_row, s_ok, s_ok2;
+  __shared__ int s_row, s_ok;
+  __shared__ int s_ok2[kGroups];
 
   CtlS* const ctl = a.ctl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -110,16 +113,27 @@ __global__ void __launch_bounds__(kLoopThreads, 3) k_loop(const LoopArgs a) {
   const long long limit = ctl->base.pivot_limit;
   int e = ctl->e_nx[(np + 1) & 1];
   const int nchunks = (int)((ld + kLoopChunk - 1) / kLoopChunk);
-  const int tiles_x = (int)((ld + 4 * kLoopThreads - 1) / (4 * kLoopThreads));
-  const int tiles_y = (mloc + 1 + kLoopRows - 1) / kLoopRows;
-  const long long ntiles = (long long)tiles_x * tiles_y;
+  const int tiles_x = (int)((ld + 4 * kGroupThreads - 1) / (4 * kGroupThreads));
+  const int group = tid / kGroupThreads, gtid = tid % kGroupThreads;
+  const int nstreams = G * kGroups;          // independent tile consumers in the grid
+  // tile height: 32 rows when that still gives every CTA several tiles, else 16, else 8, so that
+  // small (L2-resident) tableaus spread over the whole grid
+  int tile_rows = kLoopRows;
+  while (tile_rows > kLoopUnroll &&
+         (long long)tiles_x * ((mloc + tile_rows) / tile_rows) < 4ll * nstreams) tile_rows >>= 1;
+  const int tiles_y = (mloc + 1 + tile_rows - 1) / tile_rows;
+  const int ntiles = tiles_x * tiles_y;
+  __shared__ int s_tile[kGroups];
 
   for (;;) {
     const unsigned int seq = (unsigned int)(np + 1);
     const int par = seq & 1;
     double* const col = (np & 1) ? a.col1 : a.col0;      // this pivot's entering column (old values)
     double* const ncol = (np & 1) ? a.col0 : a.col1;     // next pivot's entering column
-    if (cta == 0 && tid == 0) ctl->e_nx[par ^ 1] = kNone;  // atomicMin target of phase B
+    if (cta == 0 && tid == 0) {
+      ctl->e_nx[par ^ 1] = kNone;  // atomicMin target of phase B
+      ctl->tile_ctr = nstreams;    // phase C: the first tile of every group is pre-assigned
+    }
 
     // ---------------- phase A: ratio test ----------------
     Cand best;
@@ -220,10 +234,12 @@ __global__ void __launch_bounds__(kLoopThreads, 3) k_loop(const LoopArgs a) {
     const bool i_own = !kSharded || (l >= a.row0 && l < a.row1);
     const int l_loc = l - a.row0;
     const double ce = ldcg(col + mloc);
+    bool dead = false;
     double* const rb = kSharded ? a.peers.rowbuf[a.rank] + (long long)par * ld : a.rowbuf;
     int mine = kNone;
-    for (int c = cta; c < nchunks; c += G) {
-      const long long j = (long long)c * kLoopChunk + tid;
+    // every 128-thread group takes its own 128-column chunks (the sharded flag granularity)
+    for (int c = cta * kGroups + group; c < nchunks; c += nstreams) {
+      const long long j = (long long)c * kLoopChunk + gtid;
       double r = 0.0;
       if (i_own) {
         if (j < ld) {
@@ -240,22 +256,23 @@ __global__ void __launch_bounds__(kLoopThreads, 3) k_loop(const LoopArgs a) {
         }
         if (kSharded) {
           __threadfence_system();
-          __syncthreads();
-          if (tid < a.world && tid != a.rank) st_release_sys(&a.peers.blk[tid]->row_flag[par][c], seq);
+          asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
+          if (gtid < a.world && gtid != a.rank) st_release_sys(&a.peers.blk[gtid]->row_flag[par][c], seq);
         }
       } else {
-        if (tid == 0) s_ok2 = spin_until(&a.peers.blk[a.rank]->row_flag[par][c], seq) ? 1 : 0;
-        __syncthreads();
-        if (!s_ok2) {               // a peer died: raise abort so CTAs parked in a barrier leave too
-          if (tid == 0) {
+        if (gtid == 0) s_ok2[group] = spin_until(&a.peers.blk[a.rank]->row_flag[par][c], seq) ? 1 : 0;
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
+        if (!s_ok2[group]) {       // a peer died: raise abort so CTAs parked in a barrier leave too
+          if (gtid == 0) {
             ctl->base.status = kCommTimeout;
             ctl->abort = 1;
             __threadfence();
           }
-          return;
+          dead = true;
+          break;
         }
         if (j < ld) r = ld_volatile_f64(rb + j);
-        __syncthreads();
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
       }
       if (j < n) {
         double cj = ldcg(a.T + (long long)mloc * ld + j);
@@ -263,6 +280,7 @@ __global__ void __launch_bounds__(kLoopThreads, 3) k_loop(const LoopArgs a) {
         if (cn > a.eps && (int)j < mine) mine = (int)j;
       }
     }
+    if (kSharded && __syncthreads_or(dead ? 1 : 0)) return;
     mine = warp_min_int(mine);
     if (lane == 0) sh_i[warp] = mine;
     __syncthreads();
@@ -279,54 +297,62 @@ __global__ void __launch_bounds__(kLoopThreads, 3) k_loop(const LoopArgs a) {
 
     // ---------------- phase C: tableau update ----------------
     const int l_skip = i_own ? l_loc : -1;
-    for (long long t = cta; t < ntiles; t += G) {
-      const int tx = (int)(t % tiles_x), ty = (int)(t / tiles_x);
-      const long long j0 = ((long long)tx * kLoopThreads + tid) * 4;
-      if (j0 >= ld) continue;
-      const D4 r = ldcg256(rb + j0);
-      const int ke = (e >= j0 && e < j0 + 4) ? (int)(e - j0) : -1;
-      const int k2 = (e2 != kNone && e2 >= j0 && e2 < j0 + 4) ? (int)(e2 - j0) : -1;
-      const int kb = (n >= j0 && n < j0 + 4) ? (int)(n - j0) : -1;
-      const bool special = (ke >= 0) | (k2 >= 0) | (kb >= 0);
-      const int i_begin = ty * kLoopRows;
-      const int i_end = min(i_begin + kLoopRows, mloc + 1);
-      double* base = a.T + j0;
-      for (int i = i_begin; i < i_end; i += kLoopUnroll) {
-        D4 tv[kLoopUnroll];
-        double av[kLoopUnroll];
+    // Dynamic tile queue: CTAs finish tiles at different rates (DRAM channel / die distance), so
+    // tiles beyond the first wave are claimed with an atomic counter, one claim ahead.
+    int t = cta * kGroups + group;
+    while (t < ntiles) {
+      if (gtid == 0) s_tile[group] = atomicAdd(&ctl->tile_ctr, 1);   // next tile, fetched while this one streams
+      const int tx = t % tiles_x, ty = t / tiles_x;
+      const long long j0 = ((long long)tx * kGroupThreads + gtid) * 4;
+      if (j0 < ld) {
+        const D4 r = ldcg256(rb + j0);
+        const int ke = (e >= j0 && e < j0 + 4) ? (int)(e - j0) : -1;
+        const int k2 = (e2 != kNone && e2 >= j0 && e2 < j0 + 4) ? (int)(e2 - j0) : -1;
+        const int kb = (n >= j0 && n < j0 + 4) ? (int)(n - j0) : -1;
+        const bool special = (ke >= 0) | (k2 >= 0) | (kb >= 0);
+        const int i_begin = ty * tile_rows;
+        const int i_end = min(i_begin + tile_rows, mloc + 1);
+        double* base = a.T + j0;
+        for (int i = i_begin; i < i_end; i += kLoopUnroll) {
+          D4 tv[kLoopUnroll];
+          double av[kLoopUnroll];
 #pragma unroll
-        for (int u = 0; u < kLoopUnroll; u++) {
-          int ii = i + u;
-          if (ii < i_end) {
-            av[u] = ldcg(col + ii);
-            tv[u] = ldcg256(base + (long long)ii * ld);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kLoopUnroll; u++) {
-          int ii = i + u;
-          if (ii < i_end) {
-            D4 o;
-            if (ii != l_skip) {
-              o.x = __dsub_rn(tv[u].x, __dmul_rn(av[u], r.x));
-              o.y = __dsub_rn(tv[u].y, __dmul_rn(av[u], r.y));
-              o.z = __dsub_rn(tv[u].z, __dmul_rn(av[u], r.z));
-              o.w = __dsub_rn(tv[u].w, __dmul_rn(av[u], r.w));
-              if (ke >= 0) {
-                double q = -__ddiv_rn(av[u], p);
-                if (ke == 0) o.x = q; else if (ke == 1) o.y = q; else if (ke == 2) o.z = q; else o.w = q;
-              }
-              st256(base + (long long)ii * ld, o);
-            } else {
-              o = r;
+          for (int u = 0; u < kLoopUnroll; u++) {
+            int ii = i + u;
+            if (ii < i_end) {
+              av[u] = ldcg(col + ii);
+              tv[u] = ld256(base + (long long)ii * ld);   // T is never L1-allocated: cannot be stale
             }
-            if (special) {
-              if (k2 >= 0) ncol[ii] = (k2 == 0) ? o.x : (k2 == 1) ? o.y : (k2 == 2) ? o.z : o.w;
-              if (kb >= 0) a.bcol[ii] = (kb == 0) ? o.x : (kb == 1) ? o.y : (kb == 2) ? o.z : o.w;
+          }
+#pragma unroll
+          for (int u = 0; u < kLoopUnroll; u++) {
+            int ii = i + u;
+            if (ii < i_end) {
+              D4 o;
+              if (ii != l_skip) {
+                o.x = __dsub_rn(tv[u].x, __dmul_rn(av[u], r.x));
+                o.y = __dsub_rn(tv[u].y, __dmul_rn(av[u], r.y));
+                o.z = __dsub_rn(tv[u].z, __dmul_rn(av[u], r.z));
+                o.w = __dsub_rn(tv[u].w, __dmul_rn(av[u], r.w));
+                if (ke >= 0) {
+                  double q = -__ddiv_rn(av[u], p);
+                  if (ke == 0) o.x = q; else if (ke == 1) o.y = q; else if (ke == 2) o.z = q; else o.w = q;
+                }
+                st256(base + (long long)ii * ld, o);
+              } else {
+                o = r;
+              }
+              if (special) {
+                if (k2 >= 0) ncol[ii] = (k2 == 0) ? o.x : (k2 == 1) ? o.y : (k2 == 2) ? o.z : o.w;
+                if (kb >= 0) a.bcol[ii] = (kb == 0) ? o.x : (kb == 1) ? o.y : (kb == 2) ? o.z : o.w;
+              }
             }
           }
         }
       }
+      asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
+      t = s_tile[group];
+      asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroupThreads) : "memory");
     }
     if (!grid_barrier(ctl, bar_target)) return;
     np += 1;

@@ -94,7 +94,7 @@ struct CtlS {
   int owner;          // rank that owns the leaving row of the pivot in flight
   unsigned int ticket2;
   int abort;          // persistent loop: a CTA gave up (peer timeout); everyone leaves
-  int pad_;
+  int tile_ctr;       // persistent loop: phase-C tile queue
   unsigned long long bar;     // persistent loop: grid-barrier counter
   unsigned long long upd_ns;  // persistent loop: accumulated phase-C time
 };

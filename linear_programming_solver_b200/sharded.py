@@ -137,7 +137,8 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
     import torch
 
     m, n, P = args.m, args.n, args.pivots_per_step
-    st = ShardedLPState(m, n, rank, world, synthetic_seed=args.seed, device=local_rank, time_kernels=True)
+    st = ShardedLPState(m, n, rank, world, synthetic_seed=args.seed, device=local_rank, time_kernels=True,
+                        loop_mode=args.loop_mode)
     st.attach_via(dist)
     bytes_pp_local = st.algorithmic_bytes_per_pivot()        # this rank's rows (+ objective replica)
     bytes_pp_global = 16 * (m + 1) * (n + 1)
@@ -184,7 +185,7 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
         for _ in range(3):
             barrier()
             t0 = time.perf_counter()
-            s = ShardedLPState(m, n, rank, world, A_host, b_host, c_host, device=local_rank)
+            s = ShardedLPState(m, n, rank, world, A_host, b_host, c_host, device=local_rank, loop_mode=args.loop_mode)
             s.attach_via(dist)
             r2 = s.run(Pe)
             out = (s.b, s.c, s.v, s.positions)

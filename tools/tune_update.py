@@ -17,7 +17,7 @@ def main():
     out = []
     for var in variants:
         # variant >= 100 selects the persistent loop kernel
-        kw = dict(loop_mode=2) if var >= 100 else dict(update_variant=var, loop_mode=1)
+        kw = dict(loop_mode=var - 98) if var >= 100 else dict(update_variant=var, loop_mode=1)
         st = L.LPState.synthetic_dense(m, n, 0, 1000, time_kernels=True, **kw)
         st.run(10)  # warm-up
         r = st.run(pivots)
