@@ -441,3 +441,25 @@ def test_degenerate_ties_lowest_row_wins():
     assert st.pivot_log == ref.log == osolver.trace.phase2_log
     assert st.v == float(osolver.trace.raw_v)
     assert np.array_equal(st.A, ref.A)
+
+
+# ---- parity with the reference's own arithmetic at BASELINE sizes (C decimal-15 oracle) ----------
+@pytest.mark.parametrize("m,n,seed,cap", [(300, 300, 0, -1), (250, 500, 1, -1), (1000, 1000, 0, 1200)])
+def test_sequence_vs_reference_arithmetic_mid_size(m, n, seed, cap):
+    """P2 at scale: the GPU's (entering, leaving) sequence equals the one BigDecimal(15, HALF_UP)
+    arithmetic produces (oracle/tier_d.c), objective and every b within 1e-9 relative.
+    1000 x 1000 is BASELINE config 1 (first 1200 pivots)."""
+    from oracle import tier_d
+    L = _pkg()
+    A, b, c = tier_f.gen_dense_feasible(m, n, seed)
+    ref = tier_d.TierDState(A, b, c, nthreads=tier_f.lib().tf_max_threads())
+    status, k = ref.run(cap)
+    st = L.LPState(A, b, c, m, n)
+    r = st.run(cap)
+    assert r.npivots == k
+    assert r.verdict == {tier_d.OPTIMAL: 1, tier_d.UNBOUNDED: 2, tier_d.PIVOT_CAP: 3}[status]
+    assert st.pivot_log == ref.log
+    rA, rb, rc, rv, rpos = ref.read()
+    assert abs(st.v - rv) <= REL_TOL * max(1.0, abs(rv))
+    assert np.allclose(st.b, rb, rtol=REL_TOL, atol=REL_TOL)
+    assert np.array_equal(st.positions, rpos)
