@@ -47,8 +47,11 @@ class ArrayIndexOutOfBounds : public std::out_of_range {
 struct LPStandardForm {
   int m = 0, n = 0;
   bool maximize = true;
-  std::vector<double> A;  /* row-major m x n */
+  const double* A = nullptr; /* row-major m x n view with leading dimension lda (not owned) */
+  int64_t lda = 0;
   std::vector<double> b, c;
+  std::vector<double> A_storage; /* optional owner of A */
+  void setA(std::vector<double> a) { A_storage = std::move(a); A = A_storage.data(); lda = n; }
 };
 
 /* LPState: the tableau lives on the GPU; fields are read on demand. */
@@ -157,6 +160,15 @@ int lpsolver_solve(const lps_options* opts, int m, int n, const double* A, int64
                    const double* b, double* c, int maximize, int fix_restore_index,
                    int64_t max_pivots, lpsolver_result* res, double* primal, int* phase1_log,
                    int64_t phase1_cap, int* phase2_log, int64_t phase2_cap, lps_handle* keep_state);
+
+/* LPInputReader.readLP — LPInputReader.java:52-114, the reference's text grammar (:25-31) with the
+ * `>=` negation and `=`/`==` row pairs of :189-212.  file_semantics != 0 applies readLP(File)'s
+ * rule of stopping at the first blank line (:76-86).  Returns 0 and malloc'ed arrays (release each
+ * with lpsolver_free; names are '\n'-joined in variable order), 1 with the reference's LPException
+ * message in err, or 2 for a NumberFormatException-class failure.  Host-only. */
+int lpsolver_read_lp(const char* text, int file_semantics, int* m, int* n, int* maximize, double** A,
+                     double** b, double** c, char** names, char* err, int err_cap);
+void lpsolver_free(void* p);
 
 /* BigDecimal.setScale(6, RoundingMode.HALF_UP).toString() of a binary64 value (LPSolver.java:113);
  * host-only, needs no device.  Returns the string length. */

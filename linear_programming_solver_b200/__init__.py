@@ -6,8 +6,9 @@ and a C++ host driver, `include/lpsolver_host.h`); this package is its ctypes fa
 reference's class names.  There is no CPU fallback.
 """
 from .exceptions import LPException, LpsError, SolutionException  # noqa: F401
+from .lp_input_reader import LPInputReader  # noqa: F401
 from .lp_solver import LPSolver  # noqa: F401
 from .lp_standard_form import LPStandardForm  # noqa: F401
 from .lp_state import LPState  # noqa: F401
 
-__all__ = ["LPSolver", "LPState", "LPStandardForm", "LPException", "SolutionException", "LpsError"]
+__all__ = ["LPSolver", "LPState", "LPStandardForm", "LPInputReader", "LPException", "SolutionException", "LpsError"]

@@ -89,6 +89,9 @@ SIGNATURES = {
     "lpsolver_solve": (c_int, [POINTER(LpsOptions), c_int, c_int, _dp, c_int64, _dp, _dp, c_int, c_int,
                                c_int64, POINTER(LpsolverResult), _dp, _ip, c_int64, _ip, c_int64,
                                POINTER(c_void_p)]),
+    "lpsolver_read_lp": (c_int, [c_char_p, c_int, _ip, _ip, _ip, POINTER(_dp), POINTER(_dp), POINTER(_dp),
+                                 POINTER(c_void_p), c_char_p, c_int]),
+    "lpsolver_free": (None, [c_void_p]),
     "lpsolver_set_scale6": (c_int, [c_double, c_char_p, c_int]),
     "lpsolver_min_in_b": (c_int, [_dp, c_int]),
 }

@@ -144,11 +144,11 @@ LPState LPSolver::initializeSimplex(LPStandardForm& f) {
   int k = minInB(f.b);
   if (k == -1 || f.b[(size_t)k] >= 0.0) {
     // convertIntoSlackForm, LPSolver.java:248-272
-    return LPState(f.A.data(), n, f.b.data(), f.c.data(), 0.0, m, n, options);
+    return LPState(f.A, f.lda, f.b.data(), f.c.data(), 0.0, m, n, options);
   }
   trace.used_phase1 = true;
   // convertIntoAuxLP (:283-321) happens on the device while loading
-  LPState aux = LPState::aux(f.A.data(), n, f.b.data(), m, n, options);
+  LPState aux = LPState::aux(f.A, f.lda, f.b.data(), m, n, options);
   const int n_aux = n + 1;
   const int x0_var = n;
   // solveAuxLP, :135-164: forced first pivot, then the loop (on the device)
@@ -257,8 +257,8 @@ extern "C" int lpsolver_solve(const lps_options* opts, int m, int n, const doubl
   f.m = m;
   f.n = n;
   f.maximize = maximize != 0;
-  f.A.resize((size_t)m * (size_t)n);
-  for (int i = 0; i < m; i++) std::memcpy(f.A.data() + (size_t)i * n, A + (size_t)i * lda, sizeof(double) * (size_t)n);
+  f.A = A;     // a view: the tableau is copied once, host -> HBM, inside lps_load
+  f.lda = lda;
   f.b.assign(b, b + m);
   f.c.assign(c, c + n);
   auto set_msg = [&](const char* s) { std::snprintf(res->message, sizeof(res->message), "%s", s); };

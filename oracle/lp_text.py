@@ -42,6 +42,8 @@ class LPInputReader:
         """readLP(String), LPInputReader.java:96-114."""
         self._reload()
         lines = text.split("\n")
+        while lines and lines[-1] == "":      # java.lang.String.split drops trailing empty strings
+            lines.pop()
         if len(lines) < 3:
             raise LPException("Incomplete lp")
         maximize = self._max_min(lines[0])

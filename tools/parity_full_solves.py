@@ -65,21 +65,10 @@ def main():
         rec["pos_permille"] = a.pos_permille
         rec["gpu"] = {"verdict": int(r.verdict), "pivots": int(r.npivots), "v": st.v, "device_ms": r.device_ms,
                       "wall_s": time.perf_counter() - t0, "log_sha256": digest(glog)}
-        A, b, c = tier_f.gen_dense_feasible(m, n, a.seed, a.pos_permille, nthreads=threads)
-        ref = tier_f.TierFState(A, b, c, nthreads=threads)
-        t0 = time.perf_counter()
-        status, k = ref.run()
-        first_diff = next((i for i, (x, y) in enumerate(zip(glog, ref.log)) if x != y), None)
-        rec["cpu_twin"] = {"oracle": "oracle/tier_f.c (binary64 twin, %d threads)" % threads, "status": int(status),
-                           "pivots": int(k), "v": float(ref.v[0]), "wall_s": time.perf_counter() - t0,
-                           "log_sha256": digest(ref.log)}
-        rec["identical_sequence"] = glog == ref.log
-        rec["first_divergence"] = first_diff
-        rec["v_bit_identical"] = bool(st.v == ref.v[0])
-        gb = st.b
-        rec["b_bit_identical"] = bool(np.array_equal(gb, ref.b))
-        x = st.primal(n)
-        rec["primal_nonzeros"] = int(np.count_nonzero(x))
+        rec["gpu"]["b_sha256"] = hashlib.sha256(st.b.tobytes()).hexdigest()
+        rec["primal_nonzeros"] = int(np.count_nonzero(st.primal(n)))
+        rec["note"] = ("the CPU twin of this solve takes ~20 min of host time, so it runs separately without "
+                       "holding a GPU: tools/cpu_twin_c4.py prints the same digests")
     print(json.dumps(rec, indent=1))
     if a.out:
         with open(a.out, "w") as f:
