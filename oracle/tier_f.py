@@ -258,3 +258,43 @@ def gen_dense_feasible(m: int, n: int, seed: int = 0, pos_permille: int = 1000, 
     i = np.arange(m, dtype=np.uint64)
     b = (n / 4.0) * (1.0 + u(seed, np.uint64(m) * np.uint64(n) + np.uint64(n) + i))
     return A, b, c
+
+
+def gen_mixed_rows(m: int, n: int, seed: int = 0, with_equalities: bool = True, frac_bits: int = 10):
+    """C3 family: max c.x over rows lowered the way LPInputReader lowers them
+    (LPInputReader.java:189-212), with a planted interior point x* = u(.) so the LP is feasible
+    but the origin is not (b < 0 on the '>=' rows => phase 1 is forced).
+    Rows by i mod 10: 0-5 '<=' with b = A_i.x* + s_i; 6-7 '>=' stored negated: -A_i x <= -(A_i.x* - s_i);
+    8-9 one '==' constraint stored as the +/- pair (with_equalities=False turns them into '<=' rows).
+    b is rounded to `frac_bits` fractional bits so that every input is a short dyadic number
+    (exact in binary64 AND in the decimal-15 oracle)."""
+    A = np.empty((m, n), dtype=np.float64)
+    nt = lib().tf_max_threads()
+    lib().tf_fill_u(_dp(A), n, 0, m, n, seed, 0, nt)
+    mn = np.uint64(m) * np.uint64(n)
+    j = np.arange(n, dtype=np.uint64)
+    i = np.arange(m, dtype=np.uint64)
+    c = u(seed, mn + j)
+    xstar = u(seed, mn + np.uint64(n) + np.uint64(m) + j)
+    slack = (n / 8.0) * u(seed, mn + np.uint64(2 * n) + np.uint64(m) + i)
+    scale = float(1 << frac_bits)
+    ax = A @ xstar
+    b = np.empty(m)
+    kind = np.arange(m) % 10
+    le = kind <= 5
+    ge = (kind == 6) | (kind == 7)
+    b[le] = np.round((ax[le] + slack[le]) * scale) / scale
+    A[ge] *= -1.0
+    b[ge] = np.round((-(ax[ge] - slack[ge])) * scale) / scale
+    if with_equalities:
+        for r in range(8, m - 1, 10):            # rows r, r+1: the pair +A_r x <= b, -A_r x <= -b
+            A[r + 1] = -A[r]
+            beq = np.round(ax[r] * scale) / scale
+            b[r] = beq
+            b[r + 1] = -beq
+        if m % 10 == 9:                           # a trailing unpaired row 8 stays a '<=' row
+            b[m - 1] = np.round((ax[m - 1] + slack[m - 1]) * scale) / scale
+    else:
+        eq = kind >= 8
+        b[eq] = np.round((ax[eq] + slack[eq]) * scale) / scale
+    return A, b, c

@@ -463,3 +463,48 @@ def test_sequence_vs_reference_arithmetic_mid_size(m, n, seed, cap):
     assert abs(st.v - rv) <= REL_TOL * max(1.0, abs(rv))
     assert np.allclose(st.b, rb, rtol=REL_TOL, atol=REL_TOL)
     assert np.array_equal(st.positions, rpos)
+
+
+# ---- C3 family: mixed <= / >= / == rows, phase 1 forced --------------------------------------
+@pytest.mark.parametrize("m,n,weq", [(60, 60, True), (100, 100, False), (300, 300, True), (300, 300, False),
+                                      (200, 400, True)])
+@pytest.mark.parametrize("fix", [False, True], ids=["asref", "fixed"])
+def test_mixed_rows_phase1_vs_tier_f(m, n, weq, fix):
+    """BASELINE config 2 at reduced size (the full 10,000 x 10,000 instance needs millions of pivots
+    under the first-positive rule): aux LP on the device, forced pivot, loop, degenerate pivot,
+    column drop, objective rebuild, phase 2 — P1: every index and the value equal the twin's."""
+    A, b, c = tier_f.gen_mixed_rows(m, n, 0, weq)
+    assert (b < 0).any()
+    r = tier_f.solve(A, b, c, True, fix_restore_index=fix, nthreads=4)
+    solver, verdict, value, message = _gpu_solve(dict(A=A, b=b, c=c, m=m, n=n, maximize=True), fix=fix)
+    assert verdict == r.verdict
+    assert solver.info.used_phase1
+    assert solver.info.x0_index == r.x0_index
+    assert solver.info.phase1_log == r.phase1_log
+    assert solver.info.phase2_log == r.phase2_log
+    if verdict == "optimal":
+        assert solver.info.raw_value == r.value
+        assert np.array_equal(solver.info.primal, r.primal)
+        if fix:      # with the index shift the answer is a true optimum: primal feasible, objective = c.x
+            x = solver.info.primal
+            assert (x >= -1e-9).all() and (A @ x <= b + 1e-6).all()
+            assert abs(c @ x - solver.info.raw_value) <= 1e-7 * max(1.0, abs(solver.info.raw_value))
+
+
+@pytest.mark.parametrize("m,n", [(30, 20), (60, 60)])
+def test_mixed_rows_without_equalities_vs_tier_d(m, n):
+    """P2 through phase 1 on the variant without '==' rows (SURVEY §7 hard part 1): same (e,l)
+    sequence as the reference's decimal arithmetic in both phases, objective within 1e-9."""
+    L = _pkg()
+    A, b, c = tier_f.gen_mixed_rows(m, n, 1, with_equalities=False)
+    oform = OracleForm(A.tolist(), b.tolist(), c.tolist(), m, n, True, arith=Dec15)
+    oform.key_order = "index"
+    osolver = OracleSolver(Dec15, fix_restore_index=True)
+    oval = osolver.solve(oform)
+    solver = L.LPSolver(fix_restore_index=True)
+    val = solver.solve(L.LPStandardForm(A, b, c, m, n, True))
+    assert solver.info.phase1_log == osolver.trace.phase1_log
+    assert solver.info.phase2_log == osolver.trace.phase2_log
+    ref_v = float(osolver.trace.raw_v)
+    assert abs(solver.info.raw_value - ref_v) <= REL_TOL * max(1.0, abs(ref_v))
+    assert str(val) == str(oval)
