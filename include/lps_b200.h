@@ -57,8 +57,12 @@ typedef struct {
   void *stream;         /* cudaStream_t to run on, NULL = the handle creates its own */
   int update_variant;   /* tableau-update kernel: -1 = default, >= 0 selects an alternative (tuning) */
   int loop_mode;        /* lps_run: 0 = auto, 1 = three kernels per pivot, 2 = one persistent
-                           cooperative kernel for the whole loop (grid barriers between phases) */
-  int reserved[6];
+                           cooperative kernel for the whole loop (grid barriers between phases),
+                           5 = blocked loop (block_pivots pivots per tableau pass) */
+  int block_pivots;     /* lps_run: pivots deferred between two passes over the tableau (blocked loop):
+                           0 = default (16), 1 = off (every pivot is its own pass), up to 32.  Values are
+                           bit-identical for every setting. */
+  int reserved[5];
 } lps_options;
 
 typedef struct {

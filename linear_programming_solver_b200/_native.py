@@ -23,7 +23,8 @@ LPS_RUNNING, LPS_OPTIMAL, LPS_UNBOUNDED, LPS_PIVOT_CAP = 0, 1, 2, 3
 
 class LpsOptions(Structure):
     _fields_ = [("epsilon", c_double), ("inf", c_double), ("device", c_int), ("time_kernels", c_int),
-                ("stream", c_void_p), ("update_variant", c_int), ("loop_mode", c_int), ("reserved", c_int * 6)]
+                ("stream", c_void_p), ("update_variant", c_int), ("loop_mode", c_int), ("block_pivots", c_int),
+                ("reserved", c_int * 5)]
 
 
 class LpsRunResult(Structure):

@@ -14,6 +14,7 @@
 #include "lps_kernels.cuh"
 #include "lps_sharded.cuh"
 #include "lps_loop.cuh"
+#include "lps_blocked.cuh"
 
 using namespace lps;
 
@@ -68,6 +69,13 @@ struct lps_handle_s {
   bool attached = false;
   std::vector<void*> ipc_opened;
 
+  // blocked loop (lps_blocked.cuh): up to `block` pivots deferred between two tableau passes
+  int block = 1;            // resolved from opt.block_pivots at create
+  double* acols = nullptr;  // [block][apitch] pending entering columns
+  long long apitch = 0;
+  size_t acols_cap = 0;     // doubles
+  bool flush_attr_set = false;
+
   std::vector<cudaEvent_t> ev;  // time_kernels event pool
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::string err;
@@ -76,6 +84,7 @@ struct lps_handle_s {
 namespace {
 
 constexpr int kRatioThreads = 256;
+constexpr int kDefaultBlock = 16;   // pivots per tableau pass of the blocked loop
 
 int fail(lps_handle h, int code, const char* what, cudaError_t ce = cudaSuccess) {
   if (h) {
@@ -138,7 +147,33 @@ int ensure_buffers(lps_handle h, int m, int n_cols /* n incl. any aux column */)
   h->m = m;
   h->n = n_cols;
   h->ld = ld;
+  if (h->block > 1) {
+    h->apitch = round_up((long long)m + 1 + 8, 8);   // kb_flush reads whole groups of rows
+    size_t aneed = (size_t)h->block * (size_t)h->apitch;
+    if (aneed > h->acols_cap) {
+      if (h->acols) cudaFree(h->acols);
+      h->acols = nullptr;
+      cudaError_t ce = cudaMalloc(&h->acols, aneed * sizeof(double));
+      if (ce != cudaSuccess) return fail(h, LPS_ERR_NOMEM, "cudaMalloc(pending columns)", ce);
+      h->acols_cap = aneed;
+      cudaMemsetAsync(h->acols, 0, aneed * sizeof(double), h->stream);
+    }
+  }
   return LPS_OK;
+}
+
+int ensure_comm(lps_handle h);
+
+// a single-GPU handle runs the blocked kernels as a world of one talking to itself
+int ensure_self_comm(lps_handle h) {
+  if (h->block <= 1 || h->sharded) return LPS_OK;
+  if (h->ld > (long long)kMaxChunks * kChunk) return LPS_OK;   // too wide for the flag slots: unblocked
+  h->rank = 0;
+  h->world = 1;
+  h->m_total = h->m;
+  h->row0 = 0;
+  h->row1 = h->m;
+  return ensure_comm(h);
 }
 
 int reset_state(lps_handle h) {
@@ -216,7 +251,8 @@ int prepare_next(lps_handle h) {
 
 // ---- row-sharded mode ---------------------------------------------------------------------
 int ensure_comm(lps_handle h) {
-  size_t need = sizeof(CommBlock) + 2 * (size_t)h->ld * sizeof(double);
+  // pivot-row store: 2 parity slots for the pivot-per-pass kernels, `block` slots for the blocked loop
+  size_t need = sizeof(CommBlock) + (size_t)std::max(2, h->block) * (size_t)h->ld * sizeof(double);
   if (need > h->comm_bytes) {
     if (h->attached) return fail(h, LPS_ERR_STATE, "shard: tableau grew after peers were attached");
     if (h->comm) cudaFree(h->comm);
@@ -313,14 +349,20 @@ int ensure_next_fmt(lps_handle h, bool want_nx) {
   return LPS_OK;
 }
 
+// tableau bytes per rank, computed from quantities every rank agrees on (the loop shape must be
+// the same on all ranks of a sharded solve)
+double shard_bytes(lps_handle h) {
+  const long long rows = h->sharded ? (h->m_total / h->world) : h->m;
+  return 8.0 * (double)(rows + 1) * (double)h->ld;
+}
+
 bool use_persistent(lps_handle h) {
   if (h->opt.loop_mode == 1) return false;
   if (h->opt.loop_mode >= 2) return true;
   // auto (profiles/r01_loop_modes.md): the persistent loop wins while the launch chain is a
   // visible share of a pivot; on multi-GB tableaus the hardware CTA scheduler streams ~1.5 %
   // faster than the in-kernel tile queue
-  const double bytes = 8.0 * (double)(h->m + 1) * (double)h->ld;
-  return bytes <= 2.5e9;
+  return shard_bytes(h) <= 2.5e9;
 }
 
 template <bool kSharded, int kU, int kB>
@@ -373,6 +415,139 @@ int launch_loop(lps_handle h) {
   return launch_loop_t<false, 8, 3>(h, la);
 }
 
+
+// ---- blocked loop -----------------------------------------------------------------------------
+bool use_blocked(lps_handle h) {
+  if (h->block <= 1 || !h->comm || !h->acols) return false;
+  if (h->opt.loop_mode != 0) return h->opt.loop_mode == 5;   // an explicitly requested loop shape wins
+  // below ~L2 size the pass is not the cost; the persistent pivot-per-pass loop has the shorter chain
+  return shard_bytes(h) > 64e6;
+}
+
+template <int kRows, int kUnroll, int kMinBlocks>
+int launch_flush_t(lps_handle h) {
+  const size_t smem = (size_t)h->block * 4 * kFlushThreads * sizeof(double);
+  if (!h->flush_attr_set) {
+    CK(cudaFuncSetAttribute(kb_flush<kRows, kUnroll, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)((size_t)kMaxBlock * 4 * kFlushThreads * sizeof(double))));
+    h->flush_attr_set = true;
+  }
+  dim3 grid(cdiv(h->ld, 4ll * kFlushThreads), cdiv(h->m + 1, kRows));
+  kb_flush<kRows, kUnroll, kMinBlocks><<<grid, kFlushThreads, smem, h->stream>>>(
+      h->ctls, h->T, h->ld, h->m, h->acols, h->apitch, h->peers.rowbuf[h->rank]);
+  return LPS_OK;
+}
+
+int launch_flush(lps_handle h) {
+  switch (h->opt.update_variant) {
+    default:
+    case 0: return launch_flush_t<256, 8, 3>(h);
+    case 1: return launch_flush_t<128, 8, 3>(h);
+    case 2: return launch_flush_t<512, 8, 3>(h);
+    case 3: return launch_flush_t<64, 8, 3>(h);
+    case 4: return launch_flush_t<256, 4, 4>(h);
+    case 5: return launch_flush_t<256, 8, 2>(h);
+    case 6: return launch_flush_t<1024, 8, 3>(h);
+    case 7: return launch_flush_t<128, 4, 4>(h);
+  }
+}
+
+void launch_panel_step(lps_handle h) {
+  const int colgrid = std::max(1, std::min(cdiv(h->m + 1, kColThreads), 4096));
+  kb_col<<<colgrid, kColThreads, 0, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->n, h->row0, h->acols, h->apitch,
+                                                  h->peers.rowbuf[h->rank], h->opt.epsilon, h->opt.inf,
+                                                  h->partials, h->peers, h->rank, h->world);
+  kb_row<<<cdiv(h->ld, kChunk), kChunk, 0, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->n, h->row0, h->row1, h->acols,
+                                                       h->apitch, h->opt.epsilon, h->opt.inf, h->peers, h->rank,
+                                                       h->world, h->plog, h->log_cap, h->pos2var);
+}
+
+int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
+  const long long start_pivots = h->total_pivots;
+  const int S = h->block;
+  long long launches = 0;
+  CK(cudaEventRecord(h->ev_begin, h->stream));
+  // the tableau is fully applied between calls, so the entering column comes from its objective row
+  ks_begin_run<<<1, 1, 0, h->stream>>>(h->ctls, max_pivots, 1);
+  ks_first_positive<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->ctls, h->T + (long long)h->m * h->ld, h->n,
+                                                           h->opt.epsilon);
+  launches += 2;
+  // pivots per host check: about 30 ms of device work, whole blocks
+  const double bytes = 16.0 * (double)(h->m + 1) * (double)(h->n + 1);
+  const double est_us = bytes / 5.0e6 / S + 2.0 * (double)(h->m + 1) * (double)(h->n + 1) / 12.0e6 + 14.0;
+  long long batch = (long long)(30000.0 / est_us);
+  batch = std::max((long long)S, std::min(batch, 4096ll));
+  batch = (batch / S) * S;
+  const bool timed = h->opt.time_kernels != 0;
+  const long long flushes_per_batch = batch / S + 1;
+  if (timed) {
+    while ((long long)h->ev.size() < 2 * flushes_per_batch) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->ev.push_back(e);
+    }
+  }
+  double upd_ms = 0.0;
+  long long upd_launches = 0;
+  long long remaining = (max_pivots < 0) ? -1 : (long long)max_pivots;
+  int rc = LPS_OK;
+  for (;;) {
+    // one extra panel step past the cap is what turns "cap reached" into a verdict
+    const long long todo = (remaining < 0) ? batch : std::min(batch, remaining + 1);
+    long long nflush = 0;
+    for (long long k = 0; k < todo; k++) {
+      launch_panel_step(h);
+      launches += 2;
+      if ((k + 1) % S == 0 || k == todo - 1) {
+        if (timed) cudaEventRecord(h->ev[2 * nflush], h->stream);
+        rc = launch_flush(h);
+        if (rc) return rc;
+        if (timed) cudaEventRecord(h->ev[2 * nflush + 1], h->stream);
+        nflush++;
+        launches++;
+      }
+    }
+    CK(cudaGetLastError());
+    rc = sync_ctl(h);
+    if (rc) return rc;
+    const long long done_now = h->h_ctl->npivots - h->total_pivots;
+    const long long worked = (done_now + S - 1) / S;   // flushes of this batch that had pending pivots
+    if (timed) {
+      for (long long f = 0; f < worked && f < nflush; f++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[2 * f], h->ev[2 * f + 1]) == cudaSuccess) upd_ms += ms;
+      }
+    }
+    upd_launches += std::min(worked, nflush);
+    h->total_pivots = h->h_ctl->npivots;
+    if (remaining >= 0) remaining -= done_now;
+    if (h->h_ctl->status != kRunning) break;
+  }
+  if (h->h_ctl->status == kCommTimeout) return fail(h, LPS_ERR_COMM, "shard: timed out waiting for a peer rank");
+  if (h->h_ctls->blk_pending != 0) return fail(h, LPS_ERR_STATE, "blocked loop: pivots left pending after the last pass");
+  CK(cudaEventRecord(h->ev_end, h->stream));
+  CK(cudaEventSynchronize(h->ev_end));
+  // the pivot-per-pass staging vectors (colbuf, bcol) are not maintained by this loop
+  h->next_valid = false;
+  h->col_holds = -1;
+  if (res) {
+    std::memset(res, 0, sizeof(*res));
+    res->verdict = h->h_ctl->status;
+    res->last_entering = h->h_ctl->e_cur;
+    res->last_leaving = h->h_ctl->l_cur;
+    res->npivots = h->total_pivots - start_pivots;
+    res->total_pivots = h->total_pivots;
+    double corner = 0.0;
+    CK(cudaMemcpy(&corner, h->T + (long long)h->m * h->ld + h->n, sizeof(double), cudaMemcpyDeviceToHost));
+    res->v = 0.0 - corner;
+    cudaEventElapsedTime(&res->device_ms, h->ev_begin, h->ev_end);
+    res->update_ms = (float)upd_ms;
+    res->update_launches = upd_launches;
+    res->kernel_launches = launches;
+  }
+  return LPS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -409,6 +584,8 @@ int lps_create(lps_handle* out, const lps_options* opts) {
   lps_handle h = new (std::nothrow) lps_handle_s();
   if (!h) return LPS_ERR_NOMEM;
   if (opts) h->opt = *opts; else lps_default_options(&h->opt);
+  // pivots deferred per tableau pass: 0 = default, 1 = off (pivot-per-pass kernels only)
+  h->block = (h->opt.block_pivots == 0) ? kDefaultBlock : std::max(1, std::min(h->opt.block_pivots, kMaxBlock));
   if (h->opt.device >= 0) {
     if (h->opt.device >= ndev) { delete h; return LPS_ERR_INVALID; }
     h->dev = h->opt.device;
@@ -457,6 +634,7 @@ int lps_destroy(lps_handle h) {
   if (h->h_ctls) cudaFreeHost(h->h_ctls);
   if (h->partials) cudaFree(h->partials);
   if (h->d_ops) cudaFree(h->d_ops);
+  if (h->acols) cudaFree(h->acols);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->ev_begin) cudaEventDestroy(h->ev_begin);
   if (h->ev_end) cudaEventDestroy(h->ev_end);
@@ -474,6 +652,8 @@ static int load_common(lps_handle h, int m, int n_src, int n_cols, const double*
     return fail(h, LPS_ERR_INVALID, "lps_load: bad dimensions or null buffer");
   CK(cudaSetDevice(h->dev));
   int rc = ensure_buffers(h, m, n_cols);
+  if (rc) return rc;
+  rc = ensure_self_comm(h);
   if (rc) return rc;
   const long long ld = h->ld;
   CK(cudaMemsetAsync(h->T, 0, (size_t)(m + 1) * ld * sizeof(double), h->stream));
@@ -518,6 +698,8 @@ int lps_generate_dense(lps_handle h, int m, int n, uint64_t seed, int pos_permil
   if (!h || m <= 0 || n <= 0) return fail(h, LPS_ERR_INVALID, "lps_generate_dense: bad dimensions");
   CK(cudaSetDevice(h->dev));
   int rc = ensure_buffers(h, m, n);
+  if (rc) return rc;
+  rc = ensure_self_comm(h);
   if (rc) return rc;
   dim3 grid(std::min(cdiv(h->ld, 256), 64), std::min(m + 1, 65535));
   k_generate_dense<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m, n, seed, pos_permille);
@@ -593,6 +775,7 @@ int lps_run(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   if (!h) return LPS_ERR_INVALID;
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
   CK(cudaSetDevice(h->dev));
+  if (use_blocked(h)) return run_blocked(h, max_pivots, res);
   const long long start_pivots = h->total_pivots;
   long long launches = 0;
   CK(cudaEventRecord(h->ev_begin, h->stream));

@@ -28,6 +28,7 @@ constexpr int kMaxRanks = 8;
 constexpr int kChunk = 256;           // columns per ks_scale_row CTA == flag granularity
 constexpr int kMaxChunks = 4096;      // flag slots per parity (n+1 <= 524288 at 128-column chunks)
 constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr int kMaxBlock = 32;         // blocked loop: most pivots deferred between two tableau passes
 
 enum : int { kCommTimeout = 5 };
 
@@ -97,6 +98,12 @@ struct CtlS {
   int tile_ctr;       // persistent loop: phase-C tile queue
   unsigned long long bar;     // persistent loop: grid-barrier counter
   unsigned long long upd_ns;  // persistent loop: accumulated phase-C time
+  // blocked loop (lps_blocked.cuh): pivots committed but not yet applied to the tableau
+  int blk_pending;            // 0..kMaxBlock
+  unsigned int blk_ticket;    // last-CTA-done counter of kb_flush
+  int blk_e[kMaxBlock];       // entering column of pending pivot u
+  int blk_l[kMaxBlock];       // its leaving row as a LOCAL row index, -1 if another rank owns the row
+  double blk_p[kMaxBlock];    // its pivot element
 };
 
 __global__ void ks_begin_run(CtlS* ctl, long long max_pivots, int reset_next) {

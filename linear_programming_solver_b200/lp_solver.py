@@ -39,7 +39,8 @@ class SolveInfo:
 class LPSolver:
     def __init__(self, print_rounder=None, rounder=None, epsilon=LPState.DEF_EPSILON, inf=LPState.DEF_INF,
                  fix_restore_index: bool = False, max_pivots: int = -1, device: int = -1,
-                 keep_state: bool = False, log_capacity: int = 1 << 20):
+                 keep_state: bool = False, log_capacity: int = 1 << 20, loop_mode: int = 0,
+                 block_pivots: int = 0):
         # LPSolver.java:24-58.  print_rounder / rounder (java.math.MathContext) are accepted for
         # signature compatibility; device arithmetic is IEEE binary64 round-to-nearest.
         self.print_rounder, self.rounder = print_rounder, rounder
@@ -49,6 +50,7 @@ class LPSolver:
         self.device = device
         self.keep_state = keep_state
         self.log_capacity = log_capacity
+        self.loop_mode, self.block_pivots = int(loop_mode), int(block_pivots)   # lps_options, tuning only
         self.info = SolveInfo()
 
     @staticmethod
@@ -69,6 +71,7 @@ class LPSolver:
         lib = N.load()
         opts = N.default_options()
         opts.epsilon, opts.inf, opts.device = self.epsilon, self.inf, self.device
+        opts.loop_mode, opts.block_pivots = self.loop_mode, self.block_pivots
         m, n = form.m, form.n
         A = np.ascontiguousarray(form.A, dtype=np.float64).reshape(m, n) if m * n else np.zeros((max(m, 1), max(n, 1)))
         b = np.ascontiguousarray(form.b, dtype=np.float64)

@@ -34,7 +34,8 @@ class LPState:
                  variables: Optional[Dict[int, str]] = None,
                  coefficients: Optional[Dict[str, int]] = None,
                  epsilon: float = DEF_EPSILON, inf: float = DEF_INF, device: int = -1,
-                 time_kernels: bool = False, loop_mode: int = 0, _handle=None, _aux=False):
+                 time_kernels: bool = False, loop_mode: int = 0, block_pivots: int = 0, _handle=None,
+                 _aux=False):
         self._lib = N.load()
         self._h = c_void_p()
         self._names0 = None
@@ -46,6 +47,7 @@ class LPState:
         opts = N.default_options()
         opts.epsilon, opts.inf, opts.device, opts.time_kernels = epsilon, inf, device, int(time_kernels)
         opts.loop_mode = int(loop_mode)
+        opts.block_pivots = int(block_pivots)
         rc = self._lib.lps_create(byref(self._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + self._lib.lps_status_string(rc).decode())
@@ -77,6 +79,7 @@ class LPState:
         opts.time_kernels = int(kw.get("time_kernels", False))
         opts.update_variant = int(kw.get("update_variant", -1))
         opts.loop_mode = int(kw.get("loop_mode", 0))
+        opts.block_pivots = int(kw.get("block_pivots", 0))
         rc = st._lib.lps_create(byref(st._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + st._lib.lps_status_string(rc).decode())

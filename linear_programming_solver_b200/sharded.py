@@ -51,7 +51,7 @@ class ShardedLPState(LPState):
     def __init__(self, m_total: int, n: int, rank: int, world: int, A_local=None, b_local=None, c=None,
                  v: float = 0.0, synthetic_seed: Optional[int] = None, pos_permille: int = 1000,
                  epsilon: float = LPState.DEF_EPSILON, inf: float = LPState.DEF_INF, device: int = -1,
-                 time_kernels: bool = False, loop_mode: int = 0):
+                 time_kernels: bool = False, loop_mode: int = 0, block_pivots: int = 0):
         self._lib = N.load()
         self._h = c_void_p()
         self._names0 = None
@@ -60,6 +60,7 @@ class ShardedLPState(LPState):
         opts = N.default_options()
         opts.epsilon, opts.inf, opts.device, opts.time_kernels = epsilon, inf, device, int(time_kernels)
         opts.loop_mode = int(loop_mode)
+        opts.block_pivots = int(block_pivots)
         rc = self._lib.lps_create(byref(self._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + self._lib.lps_status_string(rc).decode())

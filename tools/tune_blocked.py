@@ -1,0 +1,39 @@
+"""Time the blocked loop (pivots per tableau pass x pass-kernel tile shape) on a synthetic dense LP.
+GPU box only.  usage: python tools/tune_blocked.py [m n blocks_per_run] [--blocks 8,16,32] [--variants 0,1,2]"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import linear_programming_solver_b200 as L
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("m", type=int, nargs="?", default=20000)
+    ap.add_argument("n", type=int, nargs="?", default=40000)
+    ap.add_argument("passes", type=int, nargs="?", default=6)
+    ap.add_argument("--blocks", default="4,8,16,24,32")
+    ap.add_argument("--variants", default="0")
+    a = ap.parse_args()
+    for S in [int(x) for x in a.blocks.split(",")]:
+        for var in [int(x) for x in a.variants.split(",")]:
+            st = L.LPState.synthetic_dense(a.m, a.n, 0, 1000, time_kernels=True, loop_mode=5, block_pivots=S,
+                                           update_variant=var)
+            st.run(2 * S)  # warm-up
+            r = st.run(a.passes * S)
+            bytes_pp = st.algorithmic_bytes_per_pivot()
+            pass_ms = r.update_ms / max(r.update_launches, 1)
+            rec = dict(block=S, variant=var, m=a.m, n=a.n, pivots=int(r.npivots),
+                       pivots_per_s=1e3 * r.npivots / r.device_ms, us_per_pivot=1e3 * r.device_ms / max(r.npivots, 1),
+                       pass_ms=pass_ms, pass_dram_gbs=bytes_pp / pass_ms / 1e6 if pass_ms else None,
+                       panel_us_per_pivot=1e3 * (r.device_ms - r.update_ms) / max(r.npivots, 1),
+                       passes=int(r.update_launches), launches=int(r.kernel_launches), verdict=int(r.verdict))
+            print(json.dumps(rec), flush=True)
+            st.close()
+
+
+if __name__ == "__main__":
+    main()
