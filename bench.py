@@ -34,6 +34,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "pivots_per_sec"
 UNIT = "pivots/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the 20000x40000
+# workload, from the committed ncu --set full captures (profiles/): key = (config, pivots per launch)
+NCU_TRAFFIC = {("n1", 1): 12.756e9, ("n1", 16): 12.909e9}
 
 
 def parse_args():
@@ -51,7 +54,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", type=int, default=-1)
-    ap.add_argument("--loop-mode", type=int, default=0, help="0 auto, 1 three kernels per pivot, 2 persistent loop")
+    ap.add_argument("--loop-mode", type=int, default=0,
+                    help="0 auto (blocked loop at this size), 1 three kernels per pivot, 2 persistent loop, 5 blocked loop")
+    ap.add_argument("--block", type=int, default=0, help="pivots per tableau pass of the blocked loop (0 = library default, 1 = off)")
     return ap.parse_args()
 
 
@@ -68,6 +73,32 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def roofline_block(bytes_pp, pivots, upd_ms, upd_n, kernel_names, peak, peak_src, traffic=None):
+    """The dominant kernel's roofline entry.
+
+    One launch of the pass kernel applies `pivots/upd_n` pivots (1 for the pivot-per-pass kernels,
+    block_pivots for the blocked loop).  `achieved` is the contract's figure: ALGORITHMIC bytes per
+    launch = 16(m+1)(n+1) per pivot x pivots per launch, over the mean launch time — it exceeds the
+    HBM peak when several pivots share one pass, which is the point of the blocked loop.  The kernel's
+    real DRAM rate (one read + one write of the tableau per launch) is `dram_achieved` / `dram_frac`."""
+    upd_n = max(int(upd_n), 1)
+    avg_ms = upd_ms / upd_n
+    per_launch = pivots / upd_n
+    achieved = bytes_pp * per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+    dram = bytes_pp / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+    blocked = per_launch > 1.5
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "kernel": kernel_names[1 if blocked else 0], "launches": upd_n, "avg_ms": avg_ms,
+            "peak_source": peak_src, "pivots_per_launch": per_launch,
+            "bytes_per_launch": int(bytes_pp * per_launch), "dram_bytes_per_launch": int(bytes_pp),
+            "dram_achieved": dram, "dram_frac": dram / peak, "dram_frac_of_8tbs": dram / 8000.0,
+            "frac_of_8tbs": achieved / 8000.0,
+            "note": ("blocked loop: %.1f pivots are replayed per pass, so the pass moves 16(m+1)(n+1) bytes once for "
+                     "all of them; `achieved` counts the per-pivot algorithmic bytes (SURVEY 8d), `dram_achieved` the "
+                     "bytes the kernel really moves; at this block size the pass is FP64-issue-bound, not HBM-bound"
+                     % per_launch) if blocked else "one pivot per pass"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -81,7 +112,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -189,10 +220,10 @@ def run_ours(args):
     if world > 1:
         from linear_programming_solver_b200 import sharded
         return sharded.bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_name,
-                                     measured_peak, ClockSampler)
+                                     measured_peak, ClockSampler, roofline_block)
 
     m, n, P = args.m, args.n, args.pivots_per_step
-    kw = dict(device=local_rank, time_kernels=True, loop_mode=args.loop_mode)
+    kw = dict(device=local_rank, time_kernels=True, loop_mode=args.loop_mode, block_pivots=args.block)
     if args.variant >= 0:
         kw["update_variant"] = args.variant
     st = L.LPState.synthetic_dense(m, n, args.seed, 1000, **kw)
@@ -225,23 +256,23 @@ def run_ours(args):
                          "pick fewer steps" % (pivots, r.verdict))
     value = pivots / (dev_ms / 1e3)
     peak, peak_src = measured_peak()
-    upd_avg_ms = upd_ms / max(upd_n, 1)
-    achieved = bytes_pp / (upd_avg_ms * 1e-3) / 1e9
+    rl = roofline_block(bytes_pp, pivots, upd_ms, upd_n, ("lps::k_update", "lps::kb_flush"), peak, peak_src,
+                        traffic=NCU_TRAFFIC.get(("n1", round(pivots / max(upd_n, 1)))))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(m, n), "pivots_per_step": P, "seed": args.seed,
+                   "loop": "blocked: %.1f pivots per tableau pass" % rl["pivots_per_launch"]
+                           if rl["pivots_per_launch"] > 1.5 else "one tableau pass per pivot",
                    "l2": "tableau (6.4 GB) is far larger than the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the library's stream around each step"},
         "gpu_launches": int(launches),
         "loop_gbs": bytes_pp * pivots / (dev_ms * 1e-3) / 1e9,
         "frac_of_8tbs": bytes_pp * pivots / (dev_ms * 1e-3) / 1e9 / 8000.0,
+        "loop_dram_gbs": bytes_pp * upd_n / (dev_ms * 1e-3) / 1e9,
         "wall_s": wall,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "kernel": "lps::k_update",
-                     "launches": int(upd_n), "avg_ms": upd_avg_ms, "peak_source": peak_src,
-                     "bytes_per_launch": bytes_pp, "frac_of_8tbs": achieved / 8000.0},
+        "roofline": rl,
         "clocks": clocks,
     }
     st.close()
@@ -263,7 +294,8 @@ def run_ours(args):
         for _ in range(3):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            s = L.LPState(A_host, b_host, c_host, m, n, device=local_rank)   # H2D of the tableau
+            s = L.LPState(A_host, b_host, c_host, m, n, device=local_rank, loop_mode=args.loop_mode,
+                          block_pivots=args.block)                                # H2D of the tableau
             r = s.run(Pe)
             out_b, out_c, out_v, out_pos = s.b, s.c, s.v, s.positions         # D2H of the result
             dt = time.perf_counter() - t0

@@ -74,7 +74,7 @@ struct lps_handle_s {
   double* acols = nullptr;  // [block][apitch] pending entering columns
   long long apitch = 0;
   size_t acols_cap = 0;     // doubles
-  bool flush_attr_set = false;
+  int flush_grid = 0;       // persistent grid of kb_flush (0 = not sized yet)
 
   std::vector<cudaEvent_t> ev;  // time_kernels event pool
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -85,6 +85,7 @@ namespace {
 
 constexpr int kRatioThreads = 256;
 constexpr int kDefaultBlock = 16;   // pivots per tableau pass of the blocked loop
+constexpr int kFlushMaxBlock = 20;  // what kb_flush's double-buffered operand slices fit in 227 KB of shared memory
 
 int fail(lps_handle h, int code, const char* what, cudaError_t ce = cudaSuccess) {
   if (h) {
@@ -148,8 +149,8 @@ int ensure_buffers(lps_handle h, int m, int n_cols /* n incl. any aux column */)
   h->n = n_cols;
   h->ld = ld;
   if (h->block > 1) {
-    h->apitch = round_up((long long)m + 1 + 8, 8);   // kb_flush reads whole groups of rows
-    size_t aneed = (size_t)h->block * (size_t)h->apitch;
+    h->apitch = round_up((long long)m + 1 + 512, 8);   // kb_flush copies whole chunks of rows
+    size_t aneed = (size_t)h->block * (size_t)h->apitch + 512;
     if (aneed > h->acols_cap) {
       if (h->acols) cudaFree(h->acols);
       h->acols = nullptr;
@@ -424,31 +425,38 @@ bool use_blocked(lps_handle h) {
   return shard_bytes(h) > 64e6;
 }
 
-template <int kRows, int kUnroll, int kMinBlocks>
+template <int kLanes, int kU, int kG, bool kPre>
 int launch_flush_t(lps_handle h) {
-  const size_t smem = (size_t)h->block * 4 * kFlushThreads * sizeof(double);
-  if (!h->flush_attr_set) {
-    CK(cudaFuncSetAttribute(kb_flush<kRows, kUnroll, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)((size_t)kMaxBlock * 4 * kFlushThreads * sizeof(double))));
-    h->flush_attr_set = true;
+  constexpr int kCH = kU * kLanes * kG;
+  const size_t smem = (size_t)h->block * 2 * (kStripCols + kCH) * sizeof(double);
+  auto kern = kb_flush<kLanes, kU, kG, kPre>;
+  if (h->flush_grid == 0) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kFlushThreads * kLanes, smem);
+    if (ce != cudaSuccess || nb < 1) {
+      cudaGetLastError();
+      return fail(h, LPS_ERR_STATE, "kb_flush does not fit on an SM with this block_pivots");
+    }
+    h->flush_grid = h->sm_count;   // persistent: one CTA per SM
   }
-  dim3 grid(cdiv(h->ld, 4ll * kFlushThreads), cdiv(h->m + 1, kRows));
-  kb_flush<kRows, kUnroll, kMinBlocks><<<grid, kFlushThreads, smem, h->stream>>>(
-      h->ctls, h->T, h->ld, h->m, h->acols, h->apitch, h->peers.rowbuf[h->rank]);
+  kern<<<h->flush_grid, kFlushThreads * kLanes, smem, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->acols, h->apitch,
+                                                                 h->peers.rowbuf[h->rank]);
   return LPS_OK;
 }
 
 int launch_flush(lps_handle h) {
+  // <128-thread row-group lanes per CTA, rows per group, groups per lane per chunk, next group's loads in flight>
   switch (h->opt.update_variant) {
     default:
-    case 0: return launch_flush_t<256, 8, 3>(h);
-    case 1: return launch_flush_t<128, 8, 3>(h);
-    case 2: return launch_flush_t<512, 8, 3>(h);
-    case 3: return launch_flush_t<64, 8, 3>(h);
-    case 4: return launch_flush_t<256, 4, 4>(h);
-    case 5: return launch_flush_t<256, 8, 2>(h);
-    case 6: return launch_flush_t<1024, 8, 3>(h);
-    case 7: return launch_flush_t<128, 4, 4>(h);
+    case 0: return launch_flush_t<4, 4, 8, false>(h);   // best of the B200 sweep (profiles/)
+    case 1: return launch_flush_t<3, 8, 8, false>(h);
+    case 2: return launch_flush_t<3, 8, 4, false>(h);
+    case 3: return launch_flush_t<4, 4, 16, false>(h);
+    case 4: return launch_flush_t<4, 4, 4, false>(h);
+    case 5: return launch_flush_t<3, 4, 8, true>(h);
+    case 6: return launch_flush_t<2, 8, 8, true>(h);
+    case 7: return launch_flush_t<4, 4, 8, true>(h);
   }
 }
 
@@ -585,7 +593,7 @@ int lps_create(lps_handle* out, const lps_options* opts) {
   if (!h) return LPS_ERR_NOMEM;
   if (opts) h->opt = *opts; else lps_default_options(&h->opt);
   // pivots deferred per tableau pass: 0 = default, 1 = off (pivot-per-pass kernels only)
-  h->block = (h->opt.block_pivots == 0) ? kDefaultBlock : std::max(1, std::min(h->opt.block_pivots, kMaxBlock));
+  h->block = (h->opt.block_pivots == 0) ? kDefaultBlock : std::max(1, std::min(h->opt.block_pivots, kFlushMaxBlock));
   if (h->opt.device >= 0) {
     if (h->opt.device >= ndev) { delete h; return LPS_ERR_INVALID; }
     h->dev = h->opt.device;

@@ -263,109 +263,206 @@ kb_row(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
 }
 
 // K3 (blocked): apply all pending pivots to every local cell (objective row included) in one
-// pass.  128 threads x 4 columns = one 512-column strip; the strip's slice of the pending rows
-// sits in shared memory, the pending columns are read through L1 (warp-uniform addresses).
-// kRows rows per CTA, kUnroll rows in flight per thread (256-bit loads issued before the math).
+// pass: one 256-bit load and one 256-bit store per four cells, 2t flops per cell in between.
+//
+// One persistent CTA per SM, kLanes x 128 threads.  Work is cut into chunks of kCH rows x 512
+// columns, numbered row-band-major (consecutive chunks are neighbouring strips of the same rows, so
+// the CTAs of the grid sweep the tableau as one band: DRAM pages stay open) and claimed from an
+// atomic counter two chunks ahead.  Each 128-thread lane owns whole groups of kU rows (kU 256-bit
+// loads in flight per thread).  The operands of the replay are double-buffered in shared memory
+// and arrive by cp.async while the previous chunk is being computed:
+//   s_r [2][t][512]   the strip's slice of the pending rows
+//   s_a [2][t][kCH]   the chunk's slice of the pending columns
+// so the inner loop is LDS + DMUL/DADD only.  A group of rows that holds no pending pivot row, in a
+// thread that holds no pending pivot column, runs branch-free; anything else takes the generic
+// replay() path row by row.
 constexpr int kFlushThreads = 128;
+constexpr int kStripCols = 4 * kFlushThreads;
 
-// kUnroll consecutive entries of a pending column (warp-uniform address, 128-bit loads; the
-// column store is padded so reading past the last row stays inside the allocation)
-template <int kUnroll>
-__device__ __forceinline__ void load_a(double (&av)[kUnroll], const double* p) {
-  static_assert(kUnroll % 4 == 0, "rows in flight come in groups of four");
-#pragma unroll
-  for (int q = 0; q < kUnroll / 2; q++) {
-    const double2 v = __ldg(reinterpret_cast<const double2*>(p) + q);
-    av[2 * q + 0] = v.x; av[2 * q + 1] = v.y;
-  }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int kRows, int kUnroll, int kMinBlocks>
-__global__ void __launch_bounds__(kFlushThreads, kMinBlocks)
+template <int kLanes, int kU, int kG, bool kPre>
+__global__ void __launch_bounds__(kFlushThreads * kLanes, 1)
 kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double* __restrict__ Acols,
          long long apitch, const double* __restrict__ Rrows) {
+  constexpr int kThreads = kFlushThreads * kLanes;
+  constexpr int kCH = kU * kLanes * kG;            // rows per chunk
+  static_assert(kU % 2 == 0, "16-byte copies of the pending columns");
   const int t = ctl->blk_pending;
   if (t == 0) return;
-  extern __shared__ __align__(32) double s_r[];   // [t][4 * kFlushThreads]
+  extern __shared__ __align__(32) double smem[];
+  double* const s_r = smem;                                      // [2][t][kStripCols]
+  double* const s_a = smem + (size_t)2 * t * kStripCols;         // [2][t][kCH]
   __shared__ double s_p[kMaxBlock];
   __shared__ int s_l[kMaxBlock], s_e[kMaxBlock];
+  __shared__ long long s_claim[2], s_first[3];
   __shared__ bool s_last;
-  const int tid = threadIdx.x;
-  const long long jb = (long long)blockIdx.x * (4 * kFlushThreads);
-  const long long j0 = jb + 4 * tid;
+  const int tid = threadIdx.x, lane = tid / kFlushThreads, ltid = tid % kFlushThreads;
   if (tid < t) {
     s_l[tid] = ctl->blk_l[tid];
     s_e[tid] = ctl->blk_e[tid];
     s_p[tid] = ctl->blk_p[tid];
   }
-  if (j0 < ld) {
-    for (int u = 0; u < t; u++)
-      *reinterpret_cast<D4*>(s_r + (u * kFlushThreads + tid) * 4) =
-          *reinterpret_cast<const D4*>(Rrows + (long long)u * ld + j0);
+  const int nstrips = (int)((ld + kStripCols - 1) / kStripCols);
+  const int nrb = (mloc + 1 + kCH - 1) / kCH;                    // chunks per strip
+  const long long nchunks = (long long)nstrips * nrb;
+  unsigned long long* const queue = &ctl->blk_queue;
+  if (tid == 0) {
+    s_first[0] = (long long)atomicAdd(queue, 1ull);
+    s_first[1] = (long long)atomicAdd(queue, 1ull);
+    s_first[2] = (long long)atomicAdd(queue, 1ull);
   }
   __syncthreads();
-  const int i_begin = blockIdx.y * kRows;
-  const int i_end = min(i_begin + kRows, mloc + 1);
-  if (j0 < ld) {
-    // pending pivots whose entering column is one of my four: bit u of cmask, lane in clane
-    unsigned int cmask = 0;
-    for (int u = 0; u < t; u++)
-      if (s_e[u] >= j0 && s_e[u] < j0 + 4) cmask |= 1u << u;
-    double* base = T + j0;
-    for (int i = i_begin; i < i_end; i += kUnroll) {
-      D4 x[kUnroll];
-      // does this row group contain a pending pivot row?  (warp-uniform)
-      bool plain = (cmask == 0) && (i + kUnroll <= i_end);
-      for (int u = 0; u < t; u++) plain &= !(s_l[u] >= i && s_l[u] < i + kUnroll);
-      if (plain) {
-        // the common case: a full group of rows, no pivot row, no pivot column -> no branches
+  long long cur = s_first[0], nxt = s_first[1], nn = s_first[2];
+
+  // chunk c's operand slices -> buffer `buf`
+  auto prefetch = [&](long long c, int buf) {
+    const long long jb = (c % nstrips) * kStripCols;
+    const int i0 = (int)(c / nstrips) * kCH;
+    double* dr = s_r + (size_t)buf * t * kStripCols;
+    for (int idx = tid; idx < t * (kStripCols / 2); idx += kThreads) {
+      const int u = idx / (kStripCols / 2), q = idx % (kStripCols / 2);
+      // two planes of 16-byte pairs (x,y | z,w per thread) so that the 128-bit LDS are conflict-free
+      if (jb + 2 * q < ld)
+        cp_async16(dr + u * kStripCols + (q & 1) * (kStripCols / 2) + (q >> 1) * 2,
+                   Rrows + (long long)u * ld + jb + 2 * q);
+    }
+    double* da = s_a + (size_t)buf * t * kCH;
+    for (int idx = tid; idx < t * (kCH / 2); idx += kThreads) {
+      const int u = idx / (kCH / 2), q = idx % (kCH / 2);
+      cp_async16(da + u * kCH + 2 * q, Acols + (long long)u * apitch + i0 + 2 * q);
+    }
+    cp_async_commit();
+  };
+
+  if (cur < nchunks) prefetch(cur, 0);
+  int buf = 0;
+  bool first = true;
+  while (cur < nchunks) {
+    cp_async_wait_all();
+    __syncthreads();   // this chunk's operands have landed; everyone is done with the other buffer
+    if (!first) nn = s_claim[buf ^ 1];
+    first = false;
+    if (nxt < nchunks) prefetch(nxt, buf ^ 1);
+    if (tid == 0) s_claim[buf] = (long long)atomicAdd(queue, 1ull);   // read after the next barrier
+
+    const long long j0 = (cur % nstrips) * kStripCols + 4 * ltid;
+    if (j0 < ld) {
+      const int i0 = (int)(cur / nstrips) * kCH;
+      const int i_end = min(i0 + kCH, mloc + 1);
+      const double* sr = s_r + (size_t)buf * t * kStripCols + 2 * ltid;
+      const double* sa = s_a + (size_t)buf * t * kCH;
+      unsigned int cmask = 0;   // pending pivots whose entering column is one of my four
+      for (int u = 0; u < t; u++)
+        if (s_e[u] >= j0 && s_e[u] < j0 + 4) cmask |= 1u << u;
+      double* base = T + j0;
+      auto rvec = [&](int u) {
+        const double2 lo = *reinterpret_cast<const double2*>(sr + u * kStripCols);
+        const double2 hi = *reinterpret_cast<const double2*>(sr + u * kStripCols + kStripCols / 2);
+        D4 r;
+        r.x = lo.x; r.y = lo.y; r.z = hi.x; r.w = hi.y;
+        return r;
+      };
+      auto load_group = [&](D4 (&x)[kU], int i) {
 #pragma unroll
-        for (int k = 0; k < kUnroll; k++) x[k] = ld256(base + (long long)(i + k) * ld);
+        for (int k = 0; k < kU; k++)
+          if (i + k < i_end) x[k] = ld256(base + (long long)(i + k) * ld);
+      };
+      // replay the pending pivots on one group of rows held in registers, then store it
+      auto finish_group = [&](D4 (&x)[kU], int i, int g) {
+        // a full group without a pending pivot row, in a thread without a pending pivot column?
+        bool plain = (cmask == 0) && (i + kU <= i_end);
+        for (int u = 0; u < t; u++) plain &= !(s_l[u] >= i && s_l[u] < i + kU);
+        if (plain) {
 #pragma unroll 2
-        for (int u = 0; u < t; u++) {
-          const D4 r = *reinterpret_cast<const D4*>(s_r + (u * kFlushThreads + tid) * 4);
-          double av[kUnroll];
-          load_a<kUnroll>(av, Acols + (long long)u * apitch + i);
-#pragma unroll
-          for (int k = 0; k < kUnroll; k++) {
-            x[k].x = __dsub_rn(x[k].x, __dmul_rn(av[k], r.x));
-            x[k].y = __dsub_rn(x[k].y, __dmul_rn(av[k], r.y));
-            x[k].z = __dsub_rn(x[k].z, __dmul_rn(av[k], r.z));
-            x[k].w = __dsub_rn(x[k].w, __dmul_rn(av[k], r.w));
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < kUnroll; k++) st256(base + (long long)(i + k) * ld, x[k]);
-      } else {
-        // tail group, or a group that holds a pending pivot row / column: one row at a time
-        for (int k = 0; k < kUnroll && i + k < i_end; k++) {
-          D4 y = ld256(base + (long long)(i + k) * ld);
           for (int u = 0; u < t; u++) {
-            const D4 r = *reinterpret_cast<const D4*>(s_r + (u * kFlushThreads + tid) * 4);
-            const double a = __ldg(Acols + (long long)u * apitch + i + k);
-            const bool prow = (i + k == s_l[u]);
+            const D4 r = rvec(u);
+            double av[kU];
+#pragma unroll
+            for (int q = 0; q < kU / 2; q++) {
+              const double2 v = *reinterpret_cast<const double2*>(sa + u * kCH + g * kU + 2 * q);
+              av[2 * q] = v.x;
+              av[2 * q + 1] = v.y;
+            }
+#pragma unroll
+            for (int k = 0; k < kU; k++) {
+              x[k].x = __dsub_rn(x[k].x, __dmul_rn(av[k], r.x));
+              x[k].y = __dsub_rn(x[k].y, __dmul_rn(av[k], r.y));
+              x[k].z = __dsub_rn(x[k].z, __dmul_rn(av[k], r.z));
+              x[k].w = __dsub_rn(x[k].w, __dmul_rn(av[k], r.w));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kU; k++) st256(base + (long long)(i + k) * ld, x[k]);
+        } else {
+          for (int u = 0; u < t; u++) {
+            const D4 r = rvec(u);
+            const int lu = s_l[u];
             const int ce = ((cmask >> u) & 1u) ? (int)(s_e[u] - j0) : -1;
             const double pu = s_p[u];
-            y.x = replay(y.x, prow, ce == 0, a, r.x, pu);
-            y.y = replay(y.y, prow, ce == 1, a, r.y, pu);
-            y.z = replay(y.z, prow, ce == 2, a, r.z, pu);
-            y.w = replay(y.w, prow, ce == 3, a, r.w, pu);
+#pragma unroll
+            for (int k = 0; k < kU; k++) {
+              if (i + k < i_end) {
+                const double a = sa[u * kCH + g * kU + k];
+                const bool prow = (i + k == lu);
+                x[k].x = replay(x[k].x, prow, ce == 0, a, r.x, pu);
+                x[k].y = replay(x[k].y, prow, ce == 1, a, r.y, pu);
+                x[k].z = replay(x[k].z, prow, ce == 2, a, r.z, pu);
+                x[k].w = replay(x[k].w, prow, ce == 3, a, r.w, pu);
+              }
+            }
           }
-          st256(base + (long long)(i + k) * ld, y);
+#pragma unroll
+          for (int k = 0; k < kU; k++)
+            if (i + k < i_end) st256(base + (long long)(i + k) * ld, x[k]);
+        }
+      };
+      if (kPre) {
+        // the next group's rows are in flight while this group is computed
+        D4 x[kU], xn[kU];
+        int g = lane, i = i0 + g * kU;
+        if (i < i_end) load_group(x, i);
+        while (i < i_end) {
+          const int gn = g + kLanes, in = i0 + gn * kU;
+          const bool more = (gn < kCH / kU) && (in < i_end);
+          if (more) load_group(xn, in);
+          finish_group(x, i, g);
+          if (!more) break;
+#pragma unroll
+          for (int k = 0; k < kU; k++) x[k] = xn[k];
+          g = gn;
+          i = in;
+        }
+      } else {
+        for (int g = lane; g < kCH / kU; g += kLanes) {
+          const int i = i0 + g * kU;
+          if (i >= i_end) break;
+          D4 x[kU];
+          load_group(x, i);
+          finish_group(x, i, g);
         }
       }
     }
+    cur = nxt;
+    nxt = nn;
+    buf ^= 1;
   }
   // last CTA of the grid retires the block
   __syncthreads();
   if (tid == 0) {
     __threadfence();
     unsigned int tk = atomicAdd(&ctl->blk_ticket, 1u);
-    s_last = (tk == gridDim.x * gridDim.y - 1);
+    s_last = (tk == gridDim.x - 1);
   }
   __syncthreads();
   if (s_last && tid == 0) {
     ctl->blk_ticket = 0;
+    ctl->blk_queue = 0;
     ctl->blk_pending = 0;
   }
 }

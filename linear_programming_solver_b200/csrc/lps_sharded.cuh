@@ -101,6 +101,7 @@ struct CtlS {
   // blocked loop (lps_blocked.cuh): pivots committed but not yet applied to the tableau
   int blk_pending;            // 0..kMaxBlock
   unsigned int blk_ticket;    // last-CTA-done counter of kb_flush
+  unsigned long long blk_queue;   // kb_flush: next unclaimed chunk
   int blk_e[kMaxBlock];       // entering column of pending pivot u
   int blk_l[kMaxBlock];       // its leaving row as a LOCAL row index, -1 if another rank owns the row
   double blk_p[kMaxBlock];    // its pivot element

@@ -131,7 +131,8 @@ class ShardedLPState(LPState):
 
 
 # ---------------------------------------------------------------------------------------------
-def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_name, measured_peak, ClockSampler):
+def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_name, measured_peak, ClockSampler,
+                  roofline_block):
     """bench.py's N > 1 arm: the same LP row-sharded over `world` GPUs (strong scaling)."""
     import json
 
@@ -139,7 +140,7 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
 
     m, n, P = args.m, args.n, args.pivots_per_step
     st = ShardedLPState(m, n, rank, world, synthetic_seed=args.seed, device=local_rank, time_kernels=True,
-                        loop_mode=args.loop_mode)
+                        loop_mode=args.loop_mode, block_pivots=args.block)
     st.attach_via(dist)
     bytes_pp_local = st.algorithmic_bytes_per_pivot()        # this rank's rows (+ objective replica)
     bytes_pp_global = 16 * (m + 1) * (n + 1)
@@ -186,7 +187,8 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
         for _ in range(3):
             barrier()
             t0 = time.perf_counter()
-            s = ShardedLPState(m, n, rank, world, A_host, b_host, c_host, device=local_rank, loop_mode=args.loop_mode)
+            s = ShardedLPState(m, n, rank, world, A_host, b_host, c_host, device=local_rank, loop_mode=args.loop_mode,
+                               block_pivots=args.block)
             s.attach_via(dist)
             r2 = s.run(Pe)
             out = (s.b, s.c, s.v, s.positions)
@@ -204,12 +206,15 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
     if rank == 0:
         peak, peak_src = measured_peak()
         value = pivots / (dev_ms_max / 1e3)
-        achieved = bytes_pp_local / (upd_avg_ms * 1e-3) / 1e9
+        rl = roofline_block(bytes_pp_local, pivots, upd_avg_ms * max(upd_n, 1), upd_n,
+                            ("lps::ks_update (per rank)", "lps::kb_flush (per rank)"), peak, peak_src)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(m, n), "pivots_per_step": P, "seed": args.seed,
+                       "loop": "blocked: %.1f pivots per tableau pass" % rl["pivots_per_launch"]
+                               if rl["pivots_per_launch"] > 1.5 else "one tableau pass per pivot",
                        "sharding": "rows [k*m/G,(k+1)*m/G) per rank, objective row replicated",
                        "exchange": "ratio candidates + scaled pivot row pushed into peer memory over NVLink "
                                    "inside the kernels (no NCCL in the loop)",
@@ -218,11 +223,9 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
             "gpu_launches": int(tl[0]),
             "loop_gbs": bytes_pp_global * pivots / (dev_ms_max * 1e-3) / 1e9,
             "frac_of_8tbs_per_gpu": bytes_pp_global * pivots / (dev_ms_max * 1e-3) / 1e9 / 8000.0 / world,
+            "loop_dram_gbs_per_gpu": bytes_pp_local * upd_n / (dev_ms_max * 1e-3) / 1e9,
             "wall_s": wall,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "lps::ks_update (per rank)",
-                         "launches": int(upd_n), "avg_ms": upd_avg_ms, "peak_source": peak_src,
-                         "bytes_per_launch": bytes_pp_local, "frac_of_8tbs": achieved / 8000.0},
+            "roofline": rl,
             "clocks": clocks,
         }
         if e2e:
