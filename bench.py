@@ -6,7 +6,8 @@
 Workload (BASELINE.json configs[3], the configuration the metric is quoted on): synthetic
 dense LP, 20,000 constraints x 40,000 variables, max with <= rows (SURVEY.md §8d generator,
 seed 0), FP64 tableau of 6.4 GB resident in HBM.  One *step* = `--pivots-per-step` pivots of
-the running solve (getEntering / getLeaving / pivot on the device, LPSolver.java:101-112).
+the running solve (getEntering / getLeaving / pivot on the device, LPSolver.java:101-112); the
+default loop is the blocked one (16 pivots share one pass over the tableau, lps_blocked.cuh).
 
 The JSON line carries, beside the contract keys:
   value      pivots/s, whole job, inputs already in HBM, CUDA-event time on the library's
@@ -48,8 +49,8 @@ def parse_args():
     ap.add_argument("--m", type=int, default=20000)
     ap.add_argument("--n", type=int, default=40000)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--pivots-per-step", type=int, default=50)
-    ap.add_argument("--e2e-pivots", type=int, default=200)
+    ap.add_argument("--pivots-per-step", type=int, default=256)
+    ap.add_argument("--e2e-pivots", type=int, default=1024)
     ap.add_argument("--cpu-pivots", type=int, default=0, help="0 = sized for ~10-30 s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -58,7 +58,8 @@ typedef struct {
   int update_variant;   /* tableau-update kernel: -1 = default, >= 0 selects an alternative (tuning) */
   int loop_mode;        /* lps_run: 0 = auto, 1 = three kernels per pivot, 2 = one persistent
                            cooperative kernel for the whole loop (grid barriers between phases),
-                           5 = blocked loop (block_pivots pivots per tableau pass) */
+                           5 = blocked loop (block_pivots pivots per tableau pass) with two launches per
+                           pivot, 6 = blocked loop with one cooperative launch per block */
   int block_pivots;     /* lps_run: pivots deferred between two passes over the tableau (blocked loop):
                            0 = default (16), 1 = off (every pivot is its own pass), up to 32.  Values are
                            bit-identical for every setting. */

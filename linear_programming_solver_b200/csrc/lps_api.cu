@@ -75,6 +75,11 @@ struct lps_handle_s {
   long long apitch = 0;
   size_t acols_cap = 0;     // doubles
   int flush_grid = 0;       // persistent grid of kb_flush (0 = not sized yet)
+  int panel_grid = 0;       // cooperative grid of kb_panel (0 = not sized yet, -1 = unavailable)
+  PeerCand* ppartials = nullptr;          // kb_panel: tagged ratio-test partials, one per CTA
+  unsigned long long* pmins = nullptr;    // kb_panel: per-CTA minima
+  unsigned int* psync = nullptr;          // kb_panel: ticket / go words of its two grid-wide syncs
+  unsigned int panel_launches = 0;        // tag source: never reset, so a stale slot can never match
 
   std::vector<cudaEvent_t> ev;  // time_kernels event pool
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -85,7 +90,7 @@ namespace {
 
 constexpr int kRatioThreads = 256;
 constexpr int kDefaultBlock = 16;   // pivots per tableau pass of the blocked loop
-constexpr int kFlushMaxBlock = 20;  // what kb_flush's double-buffered operand slices fit in 227 KB of shared memory
+constexpr int kFlushMaxBlock = kPanelMax;  // kb_flush's double-buffered operand slices must fit in 227 KB of shared memory
 
 int fail(lps_handle h, int code, const char* what, cudaError_t ce = cudaSuccess) {
   if (h) {
@@ -420,7 +425,7 @@ int launch_loop(lps_handle h) {
 // ---- blocked loop -----------------------------------------------------------------------------
 bool use_blocked(lps_handle h) {
   if (h->block <= 1 || !h->comm || !h->acols) return false;
-  if (h->opt.loop_mode != 0) return h->opt.loop_mode == 5;   // an explicitly requested loop shape wins
+  if (h->opt.loop_mode != 0) return h->opt.loop_mode >= 5;   // an explicitly requested loop shape wins
   // below ~L2 size the pass is not the cost; the persistent pivot-per-pass loop has the shorter chain
   return shard_bytes(h) > 64e6;
 }
@@ -460,6 +465,67 @@ int launch_flush(lps_handle h) {
   }
 }
 
+// the whole panel of a block (up to `block` pivots) as ONE cooperative launch
+bool use_panel_kernel(lps_handle h) {
+  if (h->opt.loop_mode == 5) return false;   // 5 = blocked loop with two launches per pivot
+  if (h->panel_grid == 0) {
+    int coop = 0, nb = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->dev);
+    const size_t smem = (size_t)kPanelMax * kPanelThreads * sizeof(double);
+    cudaError_t ce = h->sharded
+        ? cudaFuncSetAttribute(kb_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        : cudaFuncSetAttribute(kb_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce == cudaSuccess)
+      ce = h->sharded ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kb_panel<true>, kPanelThreads, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kb_panel<false>, kPanelThreads, smem);
+    if (ce == cudaSuccess && coop && nb >= 1 &&
+        cudaMalloc(&h->ppartials, (size_t)h->sm_count * 128) == cudaSuccess &&
+        cudaMalloc(&h->pmins, (size_t)h->sm_count * 128) == cudaSuccess &&
+        cudaMemset(h->ppartials, 0, (size_t)h->sm_count * 128) == cudaSuccess &&
+        cudaMemset(h->pmins, 0, (size_t)h->sm_count * 128) == cudaSuccess &&
+        cudaMalloc(&h->psync, 512) == cudaSuccess && cudaMemset(h->psync, 0, 512) == cudaSuccess) {
+      h->panel_grid = h->sm_count;   // one CTA per SM; every rank of a sharded solve uses the same grid
+    } else {
+      cudaGetLastError();
+      h->panel_grid = -1;
+    }
+  }
+  return h->panel_grid > 0;
+}
+
+int launch_panel(lps_handle h) {
+  PanelArgs pa;
+  pa.ctl = h->ctls;
+  pa.T = h->T;
+  pa.ld = h->ld;
+  pa.mloc = h->m;
+  pa.n = h->n;
+  pa.row0 = h->row0;
+  pa.row1 = h->row1;
+  pa.Acols = h->acols;
+  pa.apitch = h->apitch;
+  pa.eps = h->opt.epsilon;
+  pa.inf = h->opt.inf;
+  pa.partials = h->ppartials;
+  pa.mins = h->pmins;
+  pa.syncw = h->psync;
+  // 64 tags per launch (two per pivot, at most 32 pivots); tag 0 is the cleared state
+  h->panel_launches += 1;
+  pa.tag0 = h->panel_launches * 64u;
+  pa.peers = h->peers;
+  pa.rank = h->rank;
+  pa.world = h->world;
+  pa.plog = h->plog;
+  pa.log_cap = h->log_cap;
+  pa.pos2var = h->pos2var;
+  pa.block = h->block;
+  void* args[] = {&pa};
+  const void* fn = h->sharded ? (const void*)kb_panel<true> : (const void*)kb_panel<false>;
+  CK(cudaLaunchCooperativeKernel(fn, dim3(h->panel_grid), dim3(kPanelThreads), args,
+                                 (size_t)kPanelMax * kPanelThreads * sizeof(double), h->stream));
+  return LPS_OK;
+}
+
 void launch_panel_step(lps_handle h) {
   const int colgrid = std::max(1, std::min(cdiv(h->m + 1, kColThreads), 4096));
   kb_col<<<colgrid, kColThreads, 0, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->n, h->row0, h->acols, h->apitch,
@@ -473,6 +539,7 @@ void launch_panel_step(lps_handle h) {
 int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   const long long start_pivots = h->total_pivots;
   const int S = h->block;
+  const bool panel_kernel = use_panel_kernel(h);
   long long launches = 0;
   CK(cudaEventRecord(h->ev_begin, h->stream));
   // the tableau is fully applied between calls, so the entering column comes from its objective row
@@ -504,8 +571,14 @@ int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
     const long long todo = (remaining < 0) ? batch : std::min(batch, remaining + 1);
     long long nflush = 0;
     for (long long k = 0; k < todo; k++) {
-      launch_panel_step(h);
-      launches += 2;
+      if (!panel_kernel) {
+        launch_panel_step(h);
+        launches += 2;
+      } else if (k % S == 0) {
+        rc = launch_panel(h);     // this block's pivots (it stops by itself at the cap or a verdict)
+        if (rc) return rc;
+        launches += 1;
+      }
       if ((k + 1) % S == 0 || k == todo - 1) {
         if (timed) cudaEventRecord(h->ev[2 * nflush], h->stream);
         rc = launch_flush(h);
@@ -535,6 +608,32 @@ int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   if (h->h_ctls->blk_pending != 0) return fail(h, LPS_ERR_STATE, "blocked loop: pivots left pending after the last pass");
   CK(cudaEventRecord(h->ev_end, h->stream));
   CK(cudaEventSynchronize(h->ev_end));
+#ifdef LPS_PANEL_TIMING
+  {
+    const unsigned long long* d = h->h_ctls->dbg_ns;
+    std::fprintf(stderr,
+                 "kb_panel CTA0 ns: A[loads+sync %llu | replay+div %llu | warp-reduce+sync %llu | publish %llu] gatherA %llu | "
+                 "winner %llu | B[loads+scalars+sync %llu | columns %llu | block-min+sync %llu | publish %llu] gatherB %llu | "
+                 "commit %llu  (pivots %lld)  SM clock during the panel kernels: %.0f MHz\n",
+                 d[6], d[7], d[8], d[0], d[1], d[2], d[9], d[10], d[11], d[3], d[4], d[5], (long long)h->total_pivots,
+                 d[13] ? 1e3 * (double)d[12] / (double)d[13] : 0.0);
+    if (h->pmins && h->panel_grid > 0) {
+      std::vector<unsigned long long> m((size_t)h->panel_grid * 16);
+      cudaMemcpy(m.data(), h->pmins, m.size() * 8, cudaMemcpyDeviceToHost);
+      // event times of the last pivot, relative to the earliest A-start: min / median / max over CTAs
+      const char* names[6] = {"A start", "A publish", "gather A done", "B start", "B publish", "gather B done"};
+      unsigned long long t0 = ~0ull;
+      for (int c = 0; c < h->panel_grid; c++) t0 = std::min(t0, m[(size_t)c * 16 + 1]);
+      for (int q = 0; q < 6; q++) {
+        std::vector<long long> v;
+        for (int c = 0; c < h->panel_grid; c++) v.push_back((long long)(m[(size_t)c * 16 + 1 + q] - t0));
+        std::sort(v.begin(), v.end());
+        std::fprintf(stderr, "  %-14s min %6lld  med %6lld  max %6lld ns\n", names[q], v.front(), v[v.size() / 2], v.back());
+      }
+      std::fprintf(stderr, "\n");
+    }
+  }
+#endif
   // the pivot-per-pass staging vectors (colbuf, bcol) are not maintained by this loop
   h->next_valid = false;
   h->col_holds = -1;
@@ -643,6 +742,9 @@ int lps_destroy(lps_handle h) {
   if (h->partials) cudaFree(h->partials);
   if (h->d_ops) cudaFree(h->d_ops);
   if (h->acols) cudaFree(h->acols);
+  if (h->ppartials) cudaFree(h->ppartials);
+  if (h->pmins) cudaFree(h->pmins);
+  if (h->psync) cudaFree(h->psync);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->ev_begin) cudaEventDestroy(h->ev_begin);
   if (h->ev_end) cudaEventDestroy(h->ev_end);

@@ -28,7 +28,7 @@
 // Row sharding is the same as lps_sharded.cuh (rows local, objective row replicated, candidates
 // and scaled rows by stores into peer memory); a single GPU is world == 1 talking to itself.
 #pragma once
-#include "lps_sharded.cuh"
+#include "lps_loop.cuh"
 
 namespace lps {
 
@@ -40,7 +40,70 @@ __device__ __forceinline__ double replay(double x, bool pivot_row, bool pivot_co
   return __dsub_rn(x, __dmul_rn(a, r));          // :162-164 / :177
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 constexpr int kColThreads = 128;
+constexpr int kPanelMax = 20;
+// The panel kernels replay up to kPanelMax pending pivots on a handful of cells per thread.  A
+// pending pivot whose leaving row / entering column IS the cell's row / column overwrites the
+// cell, so everything before the last such pivot is irrelevant: find it in a short rolled loop
+// (the only place a division can occur), then run the plain mul/sub chain from there, unrolled
+// and predicated.  Same operations on the surviving chain, so same bits — and a fraction of the
+// code size of an unrolled chain of three-way replay() calls (these kernels run once per pivot,
+// mostly out of a cold instruction cache).
+
+// cell (i, e) and cell (i, n) of one row: av[u] = a_u[i] (registers), re/rn = r_u[e], r_u[n]
+__device__ __forceinline__ void replay_row_pair(double& xe, double& xb, const double (&av)[kPanelMax],
+                                                const double* __restrict__ acols_i, long long apitch, int t,
+                                                int i, int e, const int* s_l, const int* s_e, const double* s_p,
+                                                const double* s_re, const double* s_rn) {
+  int ue = 0, ub = 0;
+  for (int u = 0; u < t; u++) {
+    if (i == s_l[u]) {                     // row i is pending pivot u's (scaled) leaving row
+      xe = s_re[u];
+      xb = s_rn[u];
+      ue = ub = u + 1;
+    } else if (e == s_e[u]) {              // column e was pending pivot u's entering column
+      xe = -__ddiv_rn(acols_i[(long long)u * apitch], s_p[u]);
+      ue = u + 1;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kPanelMax; u++) {
+    if (u < t) {
+      if (u >= ue) xe = __dsub_rn(xe, __dmul_rn(av[u], s_re[u]));
+      if (u >= ub) xb = __dsub_rn(xb, __dmul_rn(av[u], s_rn[u]));
+    }
+  }
+}
+
+// cell (row, j) of one column: rv[u] = r_u[j] (registers), s_a[u] = a_u[row]; row_is[u] != 0 when
+// the row is pending pivot u's leaving row
+__device__ __forceinline__ double replay_col_cell(double x, const double (&rv)[kPanelMax],
+                                                  const double* rows_j, long long ld, int t, int j,
+                                                  int row_local, const int* s_l, const int* s_e,
+                                                  const double* s_p, const double* s_a) {
+  int us = 0;
+  for (int u = 0; u < t; u++) {
+    if (row_local >= 0 && row_local == s_l[u]) {   // the row was pending pivot u's leaving row
+      x = rows_j[(long long)u * ld];
+      us = u + 1;
+    } else if (j == s_e[u]) {                      // column j was pending pivot u's entering column
+      x = -__ddiv_rn(s_a[u], s_p[u]);
+      us = u + 1;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kPanelMax; u++)
+    if (u < t && u >= us) x = __dsub_rn(x, __dmul_rn(s_a[u], rv[u]));
+  return x;
+}
+   // most pending pivots the kernels are built for (lps_create clamps block_pivots)
 
 // K1 (blocked): column e and column n of the CURRENT state for the local rows (objective row
 // included), ratio test, candidate push.  Acols[t] <- column e.
@@ -71,12 +134,12 @@ kb_col(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
     for (int i = blockIdx.x * kColThreads + threadIdx.x; i <= mloc; i += gridDim.x * kColThreads) {
       double xe = T[(long long)i * ld + e];
       double xb = T[(long long)i * ld + n];
-      for (int u = 0; u < t; u++) {
-        const double a = Acols[(long long)u * apitch + i];
-        const bool prow = (i == s_l[u]);
-        xe = replay(xe, prow, e == s_e[u], a, s_re[u], s_p[u]);
-        xb = replay(xb, prow, false, a, s_rn[u], s_p[u]);
-      }
+      // all operand loads first (one memory latency, not one per pending pivot), then the replay
+      double av[kPanelMax];
+#pragma unroll
+      for (int u = 0; u < kPanelMax; u++)
+        if (u < t) av[u] = Acols[(long long)u * apitch + i];
+      replay_row_pair(xe, xb, av, Acols + i, apitch, t, i, e, s_l, s_e, s_p, s_re, s_rn);
       acol[i] = xe;
       if (i < mloc && !(xe < eps)) {              // aie.compareTo(epsilon) < 0 -> INF   (:294-296)
         double s = __ddiv_rn(xb, xe);              // b[i].divide(aie, rounder)          (:297)
@@ -195,12 +258,20 @@ kb_row(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
   if (verdict == kRunning) {
     const double* rows = peers.rowbuf[rank];      // this rank's copy of the pending rows
     double r = 0.0;
+    // all operand loads first (one memory latency, not one per pending pivot), then the replays
+    double rv[kPanelMax];
+    double xc = 0.0;
+    if (j < ld) {
+#pragma unroll
+      for (int u = 0; u < kPanelMax; u++)
+        if (u < t) rv[u] = rows[(long long)u * ld + j];
+      if (j < n) xc = T[(long long)mloc * ld + j];
+    }
     if (i_own) {
       if (j < ld) {
         if (j <= n) {
           double x = T[(long long)lloc * ld + j];
-          for (int u = 0; u < t; u++)
-            x = replay(x, lloc == s_l[u], j == s_e[u], s_al[u], rows[(long long)u * ld + j], s_p[u]);
+          x = replay_col_cell(x, rv, rows + j, ld, t, j, lloc, s_l, s_e, s_p, s_al);
           r = (j == e) ? __ddiv_rn(1.0, p) : __ddiv_rn(x, p);        // LPState.java:139-146
         }
         for (int k = 0; k < world; k++) (peers.rowbuf[k] + (long long)t * ld)[j] = r;
@@ -220,9 +291,7 @@ kb_row(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
       if (j < ld) r = ld_volatile_f64(rows + (long long)t * ld + j);
     }
     if (j < n) {
-      double xc = T[(long long)mloc * ld + j];
-      for (int u = 0; u < t; u++)
-        xc = replay(xc, false, j == s_e[u], s_am[u], rows[(long long)u * ld + j], s_p[u]);
+      xc = replay_col_cell(xc, rv, rows + j, ld, t, j, -1, s_l, s_e, s_p, s_am);
       const double ce = Acols[(long long)t * apitch + mloc];
       double cn = (j == e) ? -__ddiv_rn(ce, p) : __dsub_rn(xc, __dmul_rn(ce, r));   // :170-178
       if (cn > eps) mine_next = j;
@@ -262,6 +331,495 @@ kb_row(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
   ctl->base.npivots = np + 1;
 }
 
+// Persistent panel: ONE cooperative launch runs the column step and the row step of every pivot
+// of a block (until the block is full, a verdict, or the pivot cap).  One CTA per SM; rows (phase
+// A) and columns (phase B) are dealt to CTAs statically, so a thread re-reads only pending-column
+// / pending-row entries its own CTA wrote.  The two global decisions of a pivot — the ratio-test
+// winner and the next entering column — are all-gathers through tagged slots: every CTA publishes
+// its partial result with a release store of a launch-unique tag and every CTA polls all the
+// slots, so a decision costs one L2 round trip after the slowest CTA instead of an atomic barrier
+// plus a reduction.  Values and decisions are the same as kb_col / kb_row, bit for bit.
+constexpr int kPanelThreads = 384;
+constexpr int kSlotStride = 128 / sizeof(PeerCand);             // slots are polled by every CTA: one L2 line each
+constexpr int kMinStride = 128 / sizeof(unsigned long long);
+
+struct PanelArgs {
+  CtlS* ctl;
+  const double* T;
+  long long ld;
+  int mloc, n, row0, row1;
+  double* Acols;
+  long long apitch;
+  double eps, inf;
+  PeerCand* partials;              // [gridDim.x * kSlotStride] ratio-test partials, tagged, one 128-byte line each
+  unsigned long long* mins;        // [gridDim.x * kMinStride] first improving column of the CTA's range
+  unsigned int* syncw;             // 4 words, one 128-byte line each: ticket A, go A, ticket B, go B
+  Peers peers;
+  int rank, world;
+  int2* plog;
+  long long log_cap;
+  int* pos2var;
+  int block;                       // pending pivots at which the launch stops (the pass comes next)
+  unsigned int tag0;               // launch-unique tag base: step s uses tag0 + 2s (+1 for phase B)
+};
+
+__device__ __forceinline__ double ldcg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ldcg_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr unsigned long long kPanelSpinNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+#ifdef LPS_PANEL_TIMING
+// phase clock of CTA 0 / thread 0, kept in registers and written out when the kernel leaves
+#define PANEL_MARK(k)                                        \
+  do {                                                       \
+    if (cta == 0 && tid == 0) {                              \
+      unsigned long long now_ = globaltimer_ns();            \
+      dbg_[k] += now_ - mark_;                               \
+      mark_ = now_;                                          \
+    }                                                        \
+  } while (0)
+#define PANEL_DUMP()                                         \
+  do {                                                       \
+    if (tid == 0) {                                          \
+      _Pragma("unroll") for (int q_ = 0; q_ < 6; q_++) a.mins[cta * kMinStride + 1 + q_] = ev_[q_]; \
+    }                                                        \
+    if (cta == 0 && tid == 0) {                              \
+      _Pragma("unroll") for (int q_ = 0; q_ < 12; q_++) ctl->dbg_ns[q_] += dbg_[q_]; \
+      ctl->dbg_ns[12] += (unsigned long long)(clock64() - clk0_);                      \
+      ctl->dbg_ns[13] += globaltimer_ns() - ns0_;                                      \
+    }                                                        \
+  } while (0)
+#else
+#define PANEL_MARK(k) do { } while (0)
+#define PANEL_DUMP() do { } while (0)
+#endif
+
+// Arrive-and-wait of the whole co-resident grid, shaped for latency: every CTA's thread 0 fences
+// and takes a ticket; the last arriver re-arms the ticket counter and stores the step's tag into
+// ONE go word that the other CTAs' thread 0 poll (relaxed loads, one acquire fence at the end).
+// Whatever the CTAs wrote before the call (their slots, their share of the pending row / column)
+// is visible to every CTA after it.  False if a peer raised ctl->abort or the wait timed out.
+__device__ __forceinline__ bool panel_sync(CtlS* ctl, unsigned int* counter, unsigned int* go, unsigned int tag) {
+  __shared__ int s_alive;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int alive = 1;
+    __threadfence();
+    const unsigned int old = atomicAdd(counter, 1u);
+    if (old == gridDim.x - 1) {
+      atomicExch(counter, 0u);
+      __threadfence();
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(tag) : "memory");
+    } else if (ld_relaxed_gpu_u32(go) != tag) {
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned int spins = 0;
+      while (ld_relaxed_gpu_u32(go) != tag) {
+        if ((++spins & 255u) == 0 &&
+            (globaltimer_ns() - t0 > kPanelSpinNs || ldcg_s32(&ctl->abort) != 0)) { alive = 0; break; }
+      }
+    }
+    // no acquire fence here: everything read across CTAs after this point is read with L1-bypassing
+    // loads (ld.global.cg / ld.volatile) that are issued only once the go word has been seen, and the
+    // producers fenced before taking their ticket, so the data is already at the L2 they are served from
+    s_alive = alive;
+  }
+  __syncthreads();
+  return s_alive != 0;
+}
+
+// one out-of-line copy of the division (the panel runs once per pivot out of a cold instruction
+// cache: code size is latency here)
+__device__ __noinline__ double ddiv_call(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+
+template <bool kSharded>
+__global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_constant__ PanelArgs a) {
+  CtlS* const ctl = a.ctl;
+  if (ctl->base.status != kRunning) return;
+  extern __shared__ __align__(16) double s_op[];     // [kPanelMax][kPanelThreads] operand staging (cp.async)
+  __shared__ double s_p[kPanelMax], s_re[kPanelMax], s_rn[kPanelMax], s_al[kPanelMax], s_am[kPanelMax];
+  __shared__ int s_l[kPanelMax], s_e[kPanelMax];
+  __shared__ PeerCand s_red[kPanelThreads / 32], s_red2[kPanelThreads / 32];
+  __shared__ int s_min[kPanelThreads / 32], s_min2[kPanelThreads / 32];
+  __shared__ double s_slack, s_pw, s_ce;
+  __shared__ int s_row, s_ok, s_ok2, s_e2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const long long ld = a.ld;
+  const int mloc = a.mloc, n = a.n;
+  long long np = ctl->base.npivots;
+  const long long limit = ctl->base.pivot_limit;
+  int t = ctl->blk_pending;
+  int e = ctl->e_nx[(np + 1) & 1];
+  if (tid < t) {
+    s_l[tid] = ctl->blk_l[tid];
+    s_e[tid] = ctl->blk_e[tid];
+    s_p[tid] = ctl->blk_p[tid];
+  }
+  // my share of the rows in phase A (objective row included) and of the columns in phase B:
+  // contiguous ranges, normally one row / one column per thread
+  const int RW = (mloc + 1 + G - 1) / G;
+  const int ilo = cta * RW, ihi = min(ilo + RW, mloc + 1);
+  const int W = (int)((((ld + G - 1) / G) + 3) / 4 * 4);
+  const long long jlo = (long long)cta * W, jhi = (jlo + W < ld) ? jlo + W : ld;
+  const double* const rows = a.peers.rowbuf[a.rank];
+  const int scribe = G - 1;   // the CTA with the smallest share writes the shared control words
+  unsigned int tag = a.tag0;
+  __syncthreads();
+#ifdef LPS_PANEL_TIMING
+  unsigned long long dbg_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long mark_ = globaltimer_ns();
+  const long long clk0_ = clock64();
+  const unsigned long long ns0_ = mark_;
+  unsigned long long ev_[6] = {0, 0, 0, 0, 0, 0};
+#endif
+
+  while (t < a.block) {
+    const unsigned int seq = (unsigned int)(np + 1);
+    const int par = seq & 1;
+    // ---------------- phase A: entering column, b column, ratio test ----------------
+#ifdef LPS_PANEL_TIMING
+    if (tid == 0) ev_[0] = globaltimer_ns();
+#endif
+    PeerCand best;
+    best.slack = a.inf; best.row = kNone; best.p = 0.0;
+    if (e != kNone) {
+      if (tid < t) {     // pending rows' entries in columns e and n (written by other CTAs: past the gather)
+        s_rn[tid] = ldcg_f64(rows + (long long)tid * ld + n);
+        s_re[tid] = ldcg_f64(rows + (long long)tid * ld + e);
+      }
+      double* acol = a.Acols + (long long)t * a.apitch;
+      for (int i0 = ilo; i0 < ihi; i0 += kPanelThreads) {   // one trip unless m + 1 > threads * gridDim.x
+        const int i = i0 + tid;
+        double xe = 0.0, xb = 0.0;
+        if (i < ihi) {
+          for (int u = 0; u < t; u++)                       // pending columns' entries of my row: all in flight at once
+            cp_async8(s_op + u * kPanelThreads + tid, a.Acols + (long long)u * a.apitch + i);
+          xe = a.T[(long long)i * ld + e];
+          xb = a.T[(long long)i * ld + n];
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();   // s_re / s_rn
+        PANEL_MARK(6);
+        if (i < ihi) {
+          for (int u = 0; u < t; u++) {
+            const double au = s_op[u * kPanelThreads + tid];
+            if (i == s_l[u]) {                              // row i is pending pivot u's scaled leaving row
+              xe = s_re[u];
+              xb = s_rn[u];
+            } else {
+              xe = (e == s_e[u]) ? -ddiv_call(au, s_p[u]) : __dsub_rn(xe, __dmul_rn(au, s_re[u]));
+              xb = __dsub_rn(xb, __dmul_rn(au, s_rn[u]));
+            }
+          }
+          acol[i] = xe;
+          if (i < mloc && !(xe < a.eps)) {                 // LPState.java:294-299
+            double sl = ddiv_call(xb, xe);
+            if (sl < best.slack) { best.slack = sl; best.row = i; best.p = xe; }
+          }
+        }
+        __syncthreads();   // s_op is reused by the next trip / phase B
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      double os = __shfl_xor_sync(0xffffffffu, best.slack, off);
+      double op = __shfl_xor_sync(0xffffffffu, best.p, off);
+      int orow = __shfl_xor_sync(0xffffffffu, best.row, off);
+      if (os < best.slack || (os == best.slack && orow < best.row)) { best.slack = os; best.p = op; best.row = orow; }
+    }
+    PANEL_MARK(7);
+    if (lane == 0) s_red[warp] = best;
+    __syncthreads();
+    PANEL_MARK(8);
+    if (tid == 0) {
+      PeerCand c = s_red[0];
+      for (int w = 1; w < kPanelThreads / 32; w++) {
+        const PeerCand o = s_red[w];
+        if (o.slack < c.slack || (o.slack == c.slack && o.row < c.row)) c = o;
+      }
+      PeerCand* mine = &a.partials[cta * kSlotStride];
+      mine->slack = c.slack;
+      mine->p = c.p;
+      mine->row = c.row;
+#ifdef LPS_PANEL_TIMING
+      ev_[1] = globaltimer_ns();
+#endif
+    }
+    PANEL_MARK(0);
+    // all-gather of the partials: grid-wide arrive-and-wait, then thread k takes CTA k's slot
+    if (!panel_sync(ctl, a.syncw + 0, a.syncw + 32, tag)) {
+      if (tid == 0) {
+        ctl->base.status = kCommTimeout;
+        ctl->abort = 1;
+        __threadfence();
+      }
+      return;
+    }
+    {
+      PeerCand c;
+      c.slack = a.inf; c.row = kNone; c.p = 0.0;
+      for (int k = tid; k < G; k += kPanelThreads) {
+        const PeerCand* src = &a.partials[k * kSlotStride];
+        PeerCand o;
+        o.slack = ldcg_f64(&src->slack);
+        o.p = ldcg_f64(&src->p);
+        o.row = ldcg_s32(&src->row);
+        if (o.slack < c.slack || (o.slack == c.slack && o.row < c.row)) c = o;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        double os = __shfl_xor_sync(0xffffffffu, c.slack, off);
+        double op = __shfl_xor_sync(0xffffffffu, c.p, off);
+        int orow = __shfl_xor_sync(0xffffffffu, c.row, off);
+        if (os < c.slack || (os == c.slack && orow < c.row)) { c.slack = os; c.p = op; c.row = orow; }
+      }
+      if (lane == 0) s_red2[warp] = c;
+      __syncthreads();
+    }
+    PANEL_MARK(1);
+#ifdef LPS_PANEL_TIMING
+    if (tid == 0) ev_[2] = globaltimer_ns();
+#endif
+    if (warp == 0) {
+      PeerCand c;
+      c.slack = a.inf; c.row = kNone; c.p = 0.0;
+      if (lane < kPanelThreads / 32) c = s_red2[lane];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        double os = __shfl_xor_sync(0xffffffffu, c.slack, off);
+        double op = __shfl_xor_sync(0xffffffffu, c.p, off);
+        int orow = __shfl_xor_sync(0xffffffffu, c.row, off);
+        if (os < c.slack || (os == c.slack && orow < c.row)) { c.slack = os; c.p = op; c.row = orow; }
+      }
+      int ok = 1;
+      if (kSharded) {
+        if (cta == 0 && lane < a.world) {   // one lane per peer (own mailbox included)
+          PeerCand* dst = &a.peers.blk[lane]->cand[par][a.rank];
+          dst->slack = c.slack;
+          dst->p = c.p;
+          dst->row = (c.row == kNone) ? kNone : a.row0 + c.row;
+          __threadfence_system();
+          st_release_sys(&dst->seq, seq);
+        }
+        PeerCand pc;
+        pc.slack = a.inf; pc.row = kNone; pc.p = 0.0;
+        if (lane < a.world) {
+          const PeerCand* src = &a.peers.blk[a.rank]->cand[par][lane];
+          ok = spin_until(&src->seq, seq) ? 1 : 0;
+          pc.slack = ld_volatile_f64(&src->slack);
+          pc.p = ld_volatile_f64(&src->p);
+          pc.row = ld_volatile_s32(&src->row);
+        }
+        ok = __all_sync(0xffffffffu, ok) ? 1 : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          double os = __shfl_xor_sync(0xffffffffu, pc.slack, off);
+          double op = __shfl_xor_sync(0xffffffffu, pc.p, off);
+          int orow = __shfl_xor_sync(0xffffffffu, pc.row, off);
+          if (os < pc.slack || (os == pc.slack && orow < pc.row)) { pc.slack = os; pc.p = op; pc.row = orow; }
+        }
+        c = pc;   // GLOBAL row from here on
+      }
+      if (lane == 0) { s_slack = c.slack; s_pw = c.p; s_row = c.row; s_ok = ok; }
+    }
+    __syncthreads();
+    const int l = (s_row == kNone) ? -1 : s_row;       // global row (== local on a single GPU)
+    const double p = s_pw;
+    PANEL_MARK(2);
+    if (kSharded && !s_ok) {        // a peer never delivered its candidate: everybody out
+      if (tid == 0) {
+        ctl->base.status = kCommTimeout;
+        ctl->abort = 1;
+        __threadfence();
+      }
+      return;
+    }
+    int verdict = kRunning;
+    if (e == kNone) verdict = kOptimal;                 // getEntering() == -1   LPSolver.java:101
+    else if (l < 0) verdict = kUnbounded;               // getLeaving() == -1    LPSolver.java:103
+    else if (np >= limit) verdict = kPivotCap;
+    if (verdict != kRunning) {
+      if (cta == scribe && tid == 0) {
+        ctl->base.status = verdict;
+        ctl->base.e_cur = (e == kNone) ? -1 : e;
+        ctl->base.l_cur = (verdict == kPivotCap) ? l : -1;
+        ctl->e_nx[par] = e;
+      }
+      PANEL_DUMP();
+      return;
+    }
+    // ---------------- phase B: leaving row, objective row, next entering column ----------------
+    const bool i_own = !kSharded || (l >= a.row0 && l < a.row1);
+    const int lloc = i_own ? l - a.row0 : -1;
+#ifdef LPS_PANEL_TIMING
+    if (tid == 0) ev_[3] = globaltimer_ns();
+#endif
+    if (tid < t) {
+      s_al[tid] = i_own ? ldcg_f64(a.Acols + (long long)tid * a.apitch + lloc) : 0.0;
+      s_am[tid] = ldcg_f64(a.Acols + (long long)tid * a.apitch + mloc);
+    }
+    if (tid == kPanelThreads - 1) s_ce = ldcg_f64(a.Acols + (long long)t * a.apitch + mloc);
+    if (tid == 0) s_ok2 = (kSharded && !i_own) ? (spin_until(&a.peers.blk[a.rank]->row_flag[par][cta], seq) ? 1 : 0) : 1;
+    int mine_next = kNone;
+    for (long long jb = jlo; jb < jhi; jb += kPanelThreads) {   // one trip unless ld > threads * gridDim.x
+      const long long j = jb + tid;
+      double xc = 0.0, x = 0.0;
+      if (j < jhi) {
+        for (int u = 0; u < t; u++)                         // pending rows' entries of my column
+          cp_async8(s_op + u * kPanelThreads + tid, rows + (long long)u * ld + j);
+        if (j < n) xc = a.T[(long long)mloc * ld + j];
+        if (i_own && j <= n) x = a.T[(long long)lloc * ld + j];
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+      __syncthreads();     // s_al / s_am / s_ce / s_ok2
+      if (jb == jlo) PANEL_MARK(9);
+      if (kSharded && !s_ok2) {
+        if (tid == 0) {
+          ctl->base.status = kCommTimeout;
+          ctl->abort = 1;
+          __threadfence();
+        }
+        return;
+      }
+      if (j < jhi) {
+        const double ce = s_ce;
+        for (int u = 0; u < t; u++) {
+          const double ru = s_op[u * kPanelThreads + tid];
+          const bool pcol = ((int)j == s_e[u]);
+          const double pu = s_p[u];
+          if (lloc >= 0 && lloc == s_l[u]) x = ru;          // the row was pending pivot u's leaving row
+          else x = pcol ? -ddiv_call(s_al[u], pu) : __dsub_rn(x, __dmul_rn(s_al[u], ru));
+          xc = pcol ? -ddiv_call(s_am[u], pu) : __dsub_rn(xc, __dmul_rn(s_am[u], ru));
+        }
+        double r = 0.0;
+        if (i_own) {
+          if (j <= n) r = ((int)j == e) ? ddiv_call(1.0, p) : ddiv_call(x, p);      // LPState.java:139-146
+          if (kSharded) {
+            for (int k = 0; k < a.world; k++) (a.peers.rowbuf[k] + (long long)t * ld)[j] = r;
+          } else {
+            (a.peers.rowbuf[0] + (long long)t * ld)[j] = r;
+          }
+        } else {
+          r = ld_volatile_f64(rows + (long long)t * ld + j);
+        }
+        if (j < n) {
+          double cn = ((int)j == e) ? -ddiv_call(ce, p) : __dsub_rn(xc, __dmul_rn(ce, r));   // :170-178
+          if (cn > a.eps && (int)j < mine_next) mine_next = (int)j;
+        }
+      }
+      __syncthreads();     // s_op is reused by the next trip / phase A
+    }
+    PANEL_MARK(10);
+    if (kSharded && i_own) {
+      __threadfence_system();
+      __syncthreads();
+      if (tid < a.world && tid != a.rank) st_release_sys(&a.peers.blk[tid]->row_flag[par][cta], seq);
+    }
+    mine_next = warp_min_int(mine_next);
+    if (lane == 0) s_min[warp] = mine_next;
+    if (tid == 0) {          // every CTA keeps its own copy of the pending pivots' scalars
+      s_e[t] = e;
+      s_l[t] = lloc;
+      s_p[t] = p;
+    }
+    __syncthreads();
+    PANEL_MARK(11);
+    if (tid == 0) {
+      int v = s_min[0];
+      for (int w = 1; w < kPanelThreads / 32; w++) v = min(v, s_min[w]);
+      a.mins[cta * kMinStride] = (unsigned long long)(unsigned int)v;
+#ifdef LPS_PANEL_TIMING
+      ev_[4] = globaltimer_ns();
+#endif
+    }
+    PANEL_MARK(3);
+    // all-gather of the per-CTA minima -> the next entering column (LPState.java:274-285)
+    if (!panel_sync(ctl, a.syncw + 64, a.syncw + 96, tag)) {
+      if (tid == 0) {
+        ctl->base.status = kCommTimeout;
+        ctl->abort = 1;
+        __threadfence();
+      }
+      return;
+    }
+    {
+      int v = kNone;
+      for (int k = tid; k < G; k += kPanelThreads) {
+        unsigned long long w;
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(w) : "l"(a.mins + k * kMinStride) : "memory");
+        v = min(v, (int)(unsigned int)(w & 0xffffffffull));
+      }
+      v = warp_min_int(v);
+      if (lane == 0) s_min2[warp] = v;
+      __syncthreads();
+      if (tid == 0) {
+        int m2 = s_min2[0];
+        for (int w = 1; w < kPanelThreads / 32; w++) m2 = min(m2, s_min2[w]);
+        s_e2 = m2;
+      }
+      __syncthreads();
+    }
+    PANEL_MARK(4);
+#ifdef LPS_PANEL_TIMING
+    if (tid == 0) ev_[5] = globaltimer_ns();
+#endif
+    const int e2 = s_e2;
+    if (cta == scribe && tid == 0) {                       // commit pivot(e, l)
+      ctl->base.e_cur = e;
+      ctl->base.l_cur = l;
+      ctl->base.p = p;
+      ctl->owner = i_own ? a.rank : -1;
+      ctl->blk_e[t] = e;
+      ctl->blk_l[t] = lloc;
+      ctl->blk_p[t] = p;
+      ctl->blk_pending = t + 1;
+      ctl->e_nx[par ^ 1] = e2;
+      a.plog[np % a.log_cap] = make_int2(e, l);
+      int tmp = a.pos2var[e];                              // exchangeIndexes, LPState.java:311-320
+      a.pos2var[e] = a.pos2var[n + l];
+      a.pos2var[n + l] = tmp;
+      ctl->base.npivots = np + 1;
+    }
+    np += 1;
+    t += 1;
+    e = e2;
+    tag += 1;
+    PANEL_MARK(5);
+  }
+  PANEL_DUMP();
+}
+
 // K3 (blocked): apply all pending pivots to every local cell (objective row included) in one
 // pass: one 256-bit load and one 256-bit store per four cells, 2t flops per cell in between.
 //
@@ -279,12 +837,6 @@ kb_row(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
 constexpr int kFlushThreads = 128;
 constexpr int kStripCols = 4 * kFlushThreads;
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int kLanes, int kU, int kG, bool kPre>
 __global__ void __launch_bounds__(kFlushThreads * kLanes, 1)

@@ -76,15 +76,30 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// spin until *flag == want; false on timeout (a dead peer must not hang the GPU)
+__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// spin until *flag == want; false on timeout (a dead peer must not hang the GPU).  The polls are
+// relaxed loads (an acquire load per poll costs an L1 invalidation each time); one acquire fence
+// when the flag has arrived orders everything read afterwards.
 __device__ __forceinline__ bool spin_until(const unsigned int* flag, unsigned int want) {
-  if (ld_acquire_sys(flag) == want) return true;
-  const unsigned long long t0 = globaltimer_ns();
-  for (;;) {
-    for (int k = 0; k < 64; k++)
-      if (ld_acquire_sys(flag) == want) return true;
-    if (globaltimer_ns() - t0 > kSpinTimeoutNs) return false;
+  bool ok = true;
+  if (ld_relaxed_sys(flag) != want) {
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+      bool hit = false;
+      for (int k = 0; k < 64 && !hit; k++) hit = (ld_relaxed_sys(flag) == want);
+      if (hit) break;
+      if (globaltimer_ns() - t0 > kSpinTimeoutNs) { ok = false; break; }
+    }
   }
+  fence_acq_rel_sys();
+  return ok;
 }
 
 // Sharded control fields live in the same Ctl (e_next is unused here):
@@ -102,6 +117,8 @@ struct CtlS {
   int blk_pending;            // 0..kMaxBlock
   unsigned int blk_ticket;    // last-CTA-done counter of kb_flush
   unsigned long long blk_queue;   // kb_flush: next unclaimed chunk
+  unsigned long long bar_base;    // kb_panel: value of `bar` when the next cooperative launch starts
+  unsigned long long dbg_ns[16];   // kb_panel phase clock of CTA 0 (LPS_PANEL_TIMING builds only)
   int blk_e[kMaxBlock];       // entering column of pending pivot u
   int blk_l[kMaxBlock];       // its leaving row as a LOCAL row index, -1 if another rank owns the row
   double blk_p[kMaxBlock];    // its pivot element
@@ -114,6 +131,7 @@ __global__ void ks_begin_run(CtlS* ctl, long long max_pivots, int reset_next) {
   ctl->ticket2 = 0;
   ctl->abort = 0;
   ctl->bar = 0;
+  ctl->bar_base = 0;
   ctl->upd_ns = 0;
   if (reset_next) ctl->e_nx[(ctl->base.npivots + 1) & 1] = kNone;
 }

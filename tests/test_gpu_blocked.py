@@ -1,6 +1,8 @@
-"""The blocked loop (lps_blocked.cuh, loop_mode=5): up to `block_pivots` pivots are deferred and
-applied in ONE pass over the tableau.  Every value must still be bit-identical to the
-pivot-per-pass kernels and to the binary64 oracle — pivot sequence, verdict, every cell.  `-m gpu`."""
+"""The blocked loop (lps_blocked.cuh): up to `block_pivots` pivots are deferred and applied in ONE
+pass over the tableau.  loop_mode=mode runs the panel as two launches per pivot (kb_col, kb_row),
+loop_mode=6 as one cooperative launch per block (kb_panel).  Every value must still be
+bit-identical to the pivot-per-pass kernels and to the binary64 oracle — pivot sequence, verdict,
+every cell.  `-m gpu`."""
 import threading
 
 import numpy as np
@@ -11,6 +13,7 @@ from oracle import tier_f
 pytestmark = pytest.mark.gpu
 
 VERDICT = {tier_f.OPTIMAL: 1, tier_f.UNBOUNDED: 2, tier_f.PIVOT_CAP: 3}
+MODES = [5, 6]
 
 
 def _L():
@@ -30,22 +33,24 @@ def _same_state(st, ref):
     assert np.array_equal(st.positions, ref.pos2var)
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("block", [2, 3, 16, 32])
 @pytest.mark.parametrize("m,n,seed", [(5, 7, 0), (12, 9, 1), (40, 80, 3), (100, 60, 4), (150, 150, 5),
                                       (257, 1030, 6), (300, 300, 7)])
-def test_blocked_bit_exact_vs_tier_f(m, n, seed, block):
+def test_blocked_bit_exact_vs_tier_f(m, n, seed, block, mode):
     L = _L()
     A, b, c = tier_f.gen_dense_feasible(m, n, seed)
     ref = tier_f.TierFState(A.copy(), b.copy(), c.copy(), nthreads=4)
     status, k = ref.run()
-    st = L.LPState(A, b, c, m, n, loop_mode=5, block_pivots=block)
+    st = L.LPState(A, b, c, m, n, loop_mode=mode, block_pivots=block)
     res = st.run()
     assert res.verdict == VERDICT[status] and res.npivots == k
     _same_state(st, ref)
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
-def test_blocked_flush_variants(variant):
+def test_blocked_flush_variants(variant, mode):
     """every tile shape of the pass kernel gives the same bits (wide and tall cases, capped)"""
     L = _L()
     from linear_programming_solver_b200.lp_state import LPState
@@ -53,19 +58,20 @@ def test_blocked_flush_variants(variant):
         A, b, c = tier_f.gen_dense_feasible(m, n, seed)
         ref = tier_f.TierFState(A.copy(), b.copy(), c.copy(), nthreads=4)
         status, k = ref.run(cap)
-        st = LPState.synthetic_dense(m, n, seed, 1000, loop_mode=5, update_variant=variant)
+        st = LPState.synthetic_dense(m, n, seed, 1000, loop_mode=mode, update_variant=variant)
         res = st.run(cap)
         assert res.verdict == VERDICT[status] and res.npivots == k
         _same_state(st, ref)
 
 
-def test_blocked_equals_pivot_per_pass_kernels():
+@pytest.mark.parametrize("mode", MODES)
+def test_blocked_equals_pivot_per_pass_kernels(mode):
     """same handle type, block_pivots=1 (three kernels per pivot) vs the blocked loop"""
     L = _L()
     m, n = 180, 420
     A, b, c = tier_f.gen_dense_feasible(m, n, 11)
     one = L.LPState(A, b, c, m, n, loop_mode=1, block_pivots=1)
-    blk = L.LPState(A, b, c, m, n, loop_mode=5, block_pivots=7)
+    blk = L.LPState(A, b, c, m, n, loop_mode=mode, block_pivots=7)
     r1, r2 = one.run(), blk.run()
     assert (r1.verdict, r1.npivots) == (r2.verdict, r2.npivots)
     assert one.pivot_log == blk.pivot_log
@@ -73,12 +79,13 @@ def test_blocked_equals_pivot_per_pass_kernels():
     assert one.v == blk.v
 
 
-def test_blocked_cap_resume_and_mixing_with_explicit_steps():
+@pytest.mark.parametrize("mode", MODES)
+def test_blocked_cap_resume_and_mixing_with_explicit_steps(mode):
     L = _L()
     A, b, c = tier_f.gen_dense_feasible(60, 60, 3)
     ref = tier_f.TierFState(A.copy(), b.copy(), c.copy())
     ref.run()
-    st = L.LPState(A, b, c, 60, 60, loop_mode=5, block_pivots=4)
+    st = L.LPState(A, b, c, 60, 60, loop_mode=mode, block_pivots=4)
     r = st.run(10)                      # 2 full blocks + a partial one
     assert r.verdict == 3 and r.npivots == 10
     assert st.pivot_log == ref.log[:10]
@@ -97,16 +104,17 @@ def test_blocked_cap_resume_and_mixing_with_explicit_steps():
     _same_state(st, ref)
 
 
-def test_blocked_immediate_and_late_verdicts():
+@pytest.mark.parametrize("mode", MODES)
+def test_blocked_immediate_and_late_verdicts(mode):
     L = _L()
     m, n = 50, 40
     A, b, c = tier_f.gen_dense_feasible(m, n, 5)
     A2 = A.copy()
     A2[:, 0] = -A2[:, 0]
-    st = L.LPState(A2, b, c, m, n, loop_mode=5)
+    st = L.LPState(A2, b, c, m, n, loop_mode=mode)
     r = st.run()
     assert r.verdict == 2 and r.npivots == 0 and r.last_entering == 0
-    st = L.LPState(A, b, -np.abs(c), m, n, loop_mode=5)
+    st = L.LPState(A, b, -np.abs(c), m, n, loop_mode=mode)
     r = st.run()
     assert r.verdict == 1 and r.npivots == 0 and st.v == 0.0
     # unbounded only after some pivots (a column with no positive entry further right)
@@ -115,13 +123,14 @@ def test_blocked_immediate_and_late_verdicts():
     ref = tier_f.TierFState(A3.copy(), b.copy(), c.copy())
     status, k = ref.run()
     assert status == tier_f.UNBOUNDED and k > 0
-    st = L.LPState(A3, b, c, m, n, loop_mode=5, block_pivots=5)
+    st = L.LPState(A3, b, c, m, n, loop_mode=mode, block_pivots=5)
     r = st.run()
     assert r.verdict == 2 and r.npivots == k
     _same_state(st, ref)
 
 
-def test_blocked_degenerate_ties_and_reentering_columns():
+@pytest.mark.parametrize("mode", MODES)
+def test_blocked_degenerate_ties_and_reentering_columns(mode):
     """exact-integer assignment-type LP: many zero ratios and ties, rows and columns that pivot
     more than once inside one block"""
     L = _L()
@@ -138,19 +147,20 @@ def test_blocked_degenerate_ties_and_reentering_columns():
     ref = tier_f.TierFState(A.copy(), b.copy(), c.copy())
     status, npiv = ref.run(5000)
     for block in (2, 8, 32):
-        st = L.LPState(A, b, c, m, n, loop_mode=5, block_pivots=block)
+        st = L.LPState(A, b, c, m, n, loop_mode=mode, block_pivots=block)
         r = st.run(5000)
         assert r.verdict == VERDICT[status] and r.npivots == npiv
         _same_state(st, ref)
 
 
-def test_blocked_mid_size_capped():
+@pytest.mark.parametrize("mode", MODES)
+def test_blocked_mid_size_capped(mode):
     L = _L()
     m = n = 1000
     A, b, c = tier_f.gen_dense_feasible(m, n, 0)
     ref = tier_f.TierFState(A.copy(), b.copy(), c.copy(), nthreads=tier_f.lib().tf_max_threads())
     ref.run(400)
-    st = L.LPState(A, b, c, m, n, loop_mode=5)
+    st = L.LPState(A, b, c, m, n, loop_mode=mode)
     r = st.run(400)
     assert r.npivots == 400 and r.verdict == 3
     _same_state(st, ref)
@@ -171,7 +181,8 @@ def test_blocked_is_the_default_for_large_tableaus():
     _same_state(st, ref)
 
 
-def test_blocked_phase1_solver_path():
+@pytest.mark.parametrize("mode", MODES)
+def test_blocked_phase1_solver_path(mode):
     """LPSolver.solve through the blocked loop: aux LP, forced pivot, restore (LPSolver.java:116-246)"""
     L = _L()
     from oracle.arith import F64
@@ -189,7 +200,7 @@ def test_blocked_phase1_solver_path():
         want = OracleSolver(F64).solve(OracleForm(A.tolist(), b.tolist(), c.tolist(), m, n, True))
     except Exception as ex:              # infeasible / unbounded: same exception type and text below
         want = ex
-    solver = L.LPSolver(loop_mode=5, block_pivots=6)
+    solver = L.LPSolver(loop_mode=mode, block_pivots=6)
     form = L.LPStandardForm(A, b, c, m, n, True)
     try:
         got = solver.solve(form)
@@ -199,21 +210,23 @@ def test_blocked_phase1_solver_path():
         assert isinstance(want, Exception) and str(ex) == str(want)
 
 
-def test_blocked_shard_world1():
+@pytest.mark.parametrize("mode", MODES)
+def test_blocked_shard_world1(mode):
     from linear_programming_solver_b200.sharded import ShardedLPState
     m, n = 257, 1030
     A, b, c = tier_f.gen_dense_feasible(m, n, 6)
     ref = tier_f.TierFState(A.copy(), b.copy(), c.copy())
     status, k = ref.run()
-    st = ShardedLPState(m, n, 0, 1, A, b, c, loop_mode=5, block_pivots=5)
+    st = ShardedLPState(m, n, 0, 1, A, b, c, loop_mode=mode, block_pivots=5)
     res = st.run()
     assert res.verdict == 1 and res.npivots == k
     assert st.pivot_log == ref.log
     assert np.array_equal(st.A, ref.A) and np.array_equal(st.b, ref.b) and np.array_equal(st.c, ref.c)
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_blocked_multi_gpu(world):
+def test_blocked_multi_gpu(world, mode):
     if _ndev() < world:
         pytest.skip("needs %d GPUs" % world)
     from linear_programming_solver_b200.sharded import ShardedLPState
@@ -221,7 +234,7 @@ def test_blocked_multi_gpu(world):
     A, b, c = tier_f.gen_dense_feasible(m, n, seed)
     ref = tier_f.TierFState(A.copy(), b.copy(), c.copy(), nthreads=4)
     status, k = ref.run()
-    shards = [ShardedLPState(m, n, r, world, synthetic_seed=seed, device=r, loop_mode=5, block_pivots=6)
+    shards = [ShardedLPState(m, n, r, world, synthetic_seed=seed, device=r, loop_mode=mode, block_pivots=6)
               for r in range(world)]
     ptrs = [s.comm_ptr() for s in shards]
     for s in shards:

@@ -17,16 +17,17 @@ def main():
     ap.add_argument("passes", type=int, nargs="?", default=6)
     ap.add_argument("--blocks", default="4,8,16,24,32")
     ap.add_argument("--variants", default="0")
+    ap.add_argument("--mode", type=int, default=6, help="5 = two launches per pivot, 6 = one cooperative launch per block")
     a = ap.parse_args()
     for S in [int(x) for x in a.blocks.split(",")]:
         for var in [int(x) for x in a.variants.split(",")]:
-            st = L.LPState.synthetic_dense(a.m, a.n, 0, 1000, time_kernels=True, loop_mode=5, block_pivots=S,
+            st = L.LPState.synthetic_dense(a.m, a.n, 0, 1000, time_kernels=True, loop_mode=a.mode, block_pivots=S,
                                            update_variant=var)
             st.run(2 * S)  # warm-up
             r = st.run(a.passes * S)
             bytes_pp = st.algorithmic_bytes_per_pivot()
             pass_ms = r.update_ms / max(r.update_launches, 1)
-            rec = dict(block=S, variant=var, m=a.m, n=a.n, pivots=int(r.npivots),
+            rec = dict(block=S, variant=var, mode=a.mode, m=a.m, n=a.n, pivots=int(r.npivots),
                        pivots_per_s=1e3 * r.npivots / r.device_ms, us_per_pivot=1e3 * r.device_ms / max(r.npivots, 1),
                        pass_ms=pass_ms, pass_dram_gbs=bytes_pp / pass_ms / 1e6 if pass_ms else None,
                        panel_us_per_pivot=1e3 * (r.device_ms - r.update_ms) / max(r.npivots, 1),
