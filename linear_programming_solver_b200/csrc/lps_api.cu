@@ -451,17 +451,26 @@ int launch_flush_t(lps_handle h) {
 }
 
 int launch_flush(lps_handle h) {
-  // <128-thread row-group lanes per CTA, rows per group, groups per lane per chunk, next group's loads in flight>
+  // <128-thread row-group lanes per CTA, rows per group, groups per lane per chunk, L2 prefetch of the next group>
   switch (h->opt.update_variant) {
-    default:
-    case 0: return launch_flush_t<4, 4, 8, false>(h);   // best of the B200 sweep (profiles/)
-    case 1: return launch_flush_t<3, 8, 8, false>(h);
-    case 2: return launch_flush_t<3, 8, 4, false>(h);
+    default: {
+      // chunk height: 256 rows is the best of the B200 sweep (profiles/) while every CTA still gets a
+      // few dozen chunks; shorter shards (8-way sharding of the 20,000-row LP) take shorter chunks, and
+      // beyond 16 pending pivots 256-row chunks no longer fit in shared memory
+      const long long strips = (h->ld + kStripCols - 1) / kStripCols;
+      const long long per_cta_256 = strips * ((h->m + 256) / 256) / std::max(1, h->sm_count);
+      if (per_cta_256 < 16) return launch_flush_t<4, 4, 4, true>(h);
+      if (h->block > 16) return launch_flush_t<4, 4, 8, true>(h);
+      return launch_flush_t<4, 4, 16, true>(h);
+    }
+    case 0: return launch_flush_t<4, 4, 16, true>(h);
+    case 1: return launch_flush_t<4, 4, 8, true>(h);
+    case 2: return launch_flush_t<4, 4, 8, false>(h);
     case 3: return launch_flush_t<4, 4, 16, false>(h);
-    case 4: return launch_flush_t<4, 4, 4, false>(h);
-    case 5: return launch_flush_t<3, 4, 8, true>(h);
-    case 6: return launch_flush_t<2, 8, 8, true>(h);
-    case 7: return launch_flush_t<4, 4, 8, true>(h);
+    case 4: return launch_flush_t<3, 8, 8, true>(h);
+    case 5: return launch_flush_t<3, 8, 8, false>(h);
+    case 6: return launch_flush_t<4, 4, 4, true>(h);
+    case 7: return launch_flush_t<3, 4, 8, true>(h);
   }
 }
 

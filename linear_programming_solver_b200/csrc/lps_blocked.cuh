@@ -838,7 +838,7 @@ constexpr int kFlushThreads = 128;
 constexpr int kStripCols = 4 * kFlushThreads;
 
 
-template <int kLanes, int kU, int kG, bool kPre>
+template <int kLanes, int kU, int kG, bool kPre>   // kPre: prefetch the lane's next group of rows into L2
 __global__ void __launch_bounds__(kFlushThreads * kLanes, 1)
 kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double* __restrict__ Acols,
          long long apitch, const double* __restrict__ Rrows) {
@@ -904,7 +904,8 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
     if (tid == 0) s_claim[buf] = (long long)atomicAdd(queue, 1ull);   // read after the next barrier
 
     const long long j0 = (cur % nstrips) * kStripCols + 4 * ltid;
-    if (j0 < ld) {
+    {
+      const bool active = (j0 < ld);     // the last strip can be narrower than the CTA
       const int i0 = (int)(cur / nstrips) * kCH;
       const int i_end = min(i0 + kCH, mloc + 1);
       const double* sr = s_r + (size_t)buf * t * kStripCols + 2 * ltid;
@@ -974,28 +975,33 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
             if (i + k < i_end) st256(base + (long long)(i + k) * ld, x[k]);
         }
       };
-      if (kPre) {
-        // the next group's rows are in flight while this group is computed
-        D4 x[kU], xn[kU];
-        int g = lane, i = i0 + g * kU;
-        if (i < i_end) load_group(x, i);
-        while (i < i_end) {
-          const int gn = g + kLanes, in = i0 + gn * kU;
-          const bool more = (gn < kCH / kU) && (in < i_end);
-          if (more) load_group(xn, in);
-          finish_group(x, i, g);
-          if (!more) break;
+      // the lane's NEXT group of rows (in this chunk, else the first one of the next chunk) is pulled
+      // into L2 while this group is replayed: prefetches hold no register and no scoreboard
+      auto prefetch_rows = [&](const double* b, int i, int iend) {
+        if ((ltid & 3) == 0) {             // one 128-byte line per four threads
 #pragma unroll
-          for (int k = 0; k < kU; k++) x[k] = xn[k];
-          g = gn;
-          i = in;
+          for (int k = 0; k < kU; k++)
+            if (i + k < iend) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (long long)(i + k) * ld));
         }
-      } else {
+      };
+      // (claiming groups dynamically inside a chunk was tried: the two lane barriers per group cost
+      // more than the imbalance they remove — profiles/r01_flush_variants.md)
+      if (active) {
         for (int g = lane; g < kCH / kU; g += kLanes) {
           const int i = i0 + g * kU;
           if (i >= i_end) break;
           D4 x[kU];
           load_group(x, i);
+          if (kPre) {
+            const int in = i + kLanes * kU;
+            if (g + kLanes < kCH / kU && in < i_end) {
+              prefetch_rows(base, in, i_end);
+            } else if (nxt < nchunks) {
+              const long long j0n = (nxt % nstrips) * kStripCols + 4 * ltid;
+              const int i0n = (int)(nxt / nstrips) * kCH;
+              if (j0n < ld) prefetch_rows(T + j0n, i0n + lane * kU, min(i0n + kCH, mloc + 1));
+            }
+          }
           finish_group(x, i, g);
         }
       }
