@@ -459,8 +459,8 @@ int launch_flush(lps_handle h) {
       // beyond 16 pending pivots 256-row chunks no longer fit in shared memory
       const long long strips = (h->ld + kStripCols - 1) / kStripCols;
       const long long per_cta_256 = strips * ((h->m + 256) / 256) / std::max(1, h->sm_count);
-      if (per_cta_256 < 16) return launch_flush_t<4, 4, 4, true>(h);
-      if (h->block > 16) return launch_flush_t<4, 4, 8, true>(h);
+      if (per_cta_256 < 12) return launch_flush_t<4, 4, 4, true>(h);
+      if (per_cta_256 < 40 || h->block > 16) return launch_flush_t<4, 4, 8, true>(h);
       return launch_flush_t<4, 4, 16, true>(h);
     }
     case 0: return launch_flush_t<4, 4, 16, true>(h);
@@ -492,7 +492,7 @@ bool use_panel_kernel(lps_handle h) {
         cudaMalloc(&h->pmins, (size_t)h->sm_count * 128) == cudaSuccess &&
         cudaMemset(h->ppartials, 0, (size_t)h->sm_count * 128) == cudaSuccess &&
         cudaMemset(h->pmins, 0, (size_t)h->sm_count * 128) == cudaSuccess &&
-        cudaMalloc(&h->psync, 512) == cudaSuccess && cudaMemset(h->psync, 0, 512) == cudaSuccess) {
+        cudaMalloc(&h->psync, 1024) == cudaSuccess && cudaMemset(h->psync, 0, 1024) == cudaSuccess) {
       h->panel_grid = h->sm_count;   // one CTA per SM; every rank of a sharded solve uses the same grid
     } else {
       cudaGetLastError();
@@ -518,6 +518,7 @@ int launch_panel(lps_handle h) {
   pa.partials = h->ppartials;
   pa.mins = h->pmins;
   pa.syncw = h->psync;
+  pa.gwin = reinterpret_cast<PeerCand*>(h->psync + 192);   // its own 128-byte line behind the five sync words
   // 64 tags per launch (two per pivot, at most 32 pivots); tag 0 is the cleared state
   h->panel_launches += 1;
   pa.tag0 = h->panel_launches * 64u;

@@ -353,7 +353,8 @@ struct PanelArgs {
   double eps, inf;
   PeerCand* partials;              // [gridDim.x * kSlotStride] ratio-test partials, tagged, one 128-byte line each
   unsigned long long* mins;        // [gridDim.x * kMinStride] first improving column of the CTA's range
-  unsigned int* syncw;             // 4 words, one 128-byte line each: ticket A, go A, ticket B, go B
+  unsigned int* syncw;             // words on their own 128-byte lines: ticket A, go A, ticket B, go B, go W
+  PeerCand* gwin;                  // sharded: the cross-rank winner, published by CTA 0 for the other CTAs
   Peers peers;
   int rank, world;
   int2* plog;
@@ -623,32 +624,61 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
       }
       int ok = 1;
       if (kSharded) {
-        if (cta == 0 && lane < a.world) {   // one lane per peer (own mailbox included)
-          PeerCand* dst = &a.peers.blk[lane]->cand[par][a.rank];
-          dst->slack = c.slack;
-          dst->p = c.p;
-          dst->row = (c.row == kNone) ? kNone : a.row0 + c.row;
-          __threadfence_system();
-          st_release_sys(&dst->seq, seq);
-        }
-        PeerCand pc;
-        pc.slack = a.inf; pc.row = kNone; pc.p = 0.0;
-        if (lane < a.world) {
-          const PeerCand* src = &a.peers.blk[a.rank]->cand[par][lane];
-          ok = spin_until(&src->seq, seq) ? 1 : 0;
-          pc.slack = ld_volatile_f64(&src->slack);
-          pc.p = ld_volatile_f64(&src->p);
-          pc.row = ld_volatile_s32(&src->row);
-        }
-        ok = __all_sync(0xffffffffu, ok) ? 1 : 0;
+        // only CTA 0 talks to the peers (148 CTAs polling the same two mailbox lines would fight the
+        // incoming NVLink writes); it hands the cross-rank winner to the other CTAs through one go word
+        if (cta == 0) {
+          if (lane < a.world) {   // one lane per peer (own mailbox included)
+            PeerCand* dst = &a.peers.blk[lane]->cand[par][a.rank];
+            dst->slack = c.slack;
+            dst->p = c.p;
+            dst->row = (c.row == kNone) ? kNone : a.row0 + c.row;
+            st_release_sys(&dst->seq, seq);
+          }
+          PeerCand pc;
+          pc.slack = a.inf; pc.row = kNone; pc.p = 0.0;
+          if (lane < a.world) {
+            const PeerCand* src = &a.peers.blk[a.rank]->cand[par][lane];
+            ok = spin_until<false>(&src->seq, seq) ? 1 : 0;
+            pc.slack = ld_volatile_f64(&src->slack);
+            pc.p = ld_volatile_f64(&src->p);
+            pc.row = ld_volatile_s32(&src->row);
+          }
+          ok = __all_sync(0xffffffffu, ok) ? 1 : 0;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          double os = __shfl_xor_sync(0xffffffffu, pc.slack, off);
-          double op = __shfl_xor_sync(0xffffffffu, pc.p, off);
-          int orow = __shfl_xor_sync(0xffffffffu, pc.row, off);
-          if (os < pc.slack || (os == pc.slack && orow < pc.row)) { pc.slack = os; pc.p = op; pc.row = orow; }
+          for (int off = 16; off > 0; off >>= 1) {
+            double os = __shfl_xor_sync(0xffffffffu, pc.slack, off);
+            double op = __shfl_xor_sync(0xffffffffu, pc.p, off);
+            int orow = __shfl_xor_sync(0xffffffffu, pc.row, off);
+            if (os < pc.slack || (os == pc.slack && orow < pc.row)) { pc.slack = os; pc.p = op; pc.row = orow; }
+          }
+          c = pc;   // GLOBAL row from here on
+          if (lane == 0) {
+            if (ok) {
+              a.gwin->slack = c.slack;
+              a.gwin->p = c.p;
+              a.gwin->row = c.row;
+              st_release_gpu_u32(a.syncw + 128, tag);
+            } else {
+              ctl->base.status = kCommTimeout;
+              ctl->abort = 1;
+              __threadfence();
+            }
+          }
+        } else {
+          if (lane == 0) {
+            if (ld_relaxed_gpu_u32(a.syncw + 128) != tag) {
+              const unsigned long long t0 = globaltimer_ns();
+              unsigned int spins = 0;
+              while (ld_relaxed_gpu_u32(a.syncw + 128) != tag) {
+                if ((++spins & 255u) == 0 &&
+                    (globaltimer_ns() - t0 > kPanelSpinNs || ldcg_s32(&ctl->abort) != 0)) { ok = 0; break; }
+              }
+            }
+            c.slack = ldcg_f64(&a.gwin->slack);
+            c.p = ldcg_f64(&a.gwin->p);
+            c.row = ldcg_s32(&a.gwin->row);
+          }
         }
-        c = pc;   // GLOBAL row from here on
       }
       if (lane == 0) { s_slack = c.slack; s_pw = c.p; s_row = c.row; s_ok = ok; }
     }
@@ -689,7 +719,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
       s_am[tid] = ldcg_f64(a.Acols + (long long)tid * a.apitch + mloc);
     }
     if (tid == kPanelThreads - 1) s_ce = ldcg_f64(a.Acols + (long long)t * a.apitch + mloc);
-    if (tid == 0) s_ok2 = (kSharded && !i_own) ? (spin_until(&a.peers.blk[a.rank]->row_flag[par][cta], seq) ? 1 : 0) : 1;
+    if (tid == 0) s_ok2 = (kSharded && !i_own) ? (spin_until<false>(&a.peers.blk[a.rank]->row_flag[par][cta], seq) ? 1 : 0) : 1;
     int mine_next = kNone;
     for (long long jb = jlo; jb < jhi; jb += kPanelThreads) {   // one trip unless ld > threads * gridDim.x
       const long long j = jb + tid;
@@ -742,8 +772,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
     }
     PANEL_MARK(10);
     if (kSharded && i_own) {
-      __threadfence_system();
-      __syncthreads();
+      __syncthreads();     // the CTA's stores into the peers' row stores, then one release per peer
       if (tid < a.world && tid != a.rank) st_release_sys(&a.peers.blk[tid]->row_flag[par][cta], seq);
     }
     mine_next = warp_min_int(mine_next);

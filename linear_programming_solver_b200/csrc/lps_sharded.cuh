@@ -87,6 +87,7 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 // spin until *flag == want; false on timeout (a dead peer must not hang the GPU).  The polls are
 // relaxed loads (an acquire load per poll costs an L1 invalidation each time); one acquire fence
 // when the flag has arrived orders everything read afterwards.
+template <bool kAcquireFence = true>
 __device__ __forceinline__ bool spin_until(const unsigned int* flag, unsigned int want) {
   bool ok = true;
   if (ld_relaxed_sys(flag) != want) {
@@ -98,7 +99,9 @@ __device__ __forceinline__ bool spin_until(const unsigned int* flag, unsigned in
       if (globaltimer_ns() - t0 > kSpinTimeoutNs) { ok = false; break; }
     }
   }
-  fence_acq_rel_sys();
+  // callers that go on to read only with L1-bypassing loads (ld.volatile / ld.cg) may skip the fence:
+  // the producer fenced before the flag, so the data is in this GPU's memory by the time the flag is
+  if (kAcquireFence) fence_acq_rel_sys();
   return ok;
 }
 
