@@ -111,6 +111,15 @@ int lps_load_aux(lps_handle h, int m, int n, const double *A, int64_t lda, const
  * A_ij = u(i*n+j), c_j = ±u(mn+j), b_i = (n/4)(1+u(mn+n+i)).  rows [row0,row1) only are
  * materialised when the handle is a row shard (row0=0,row1=m for a single GPU). */
 int lps_generate_dense(lps_handle h, int m, int n, uint64_t seed, int pos_permille);
+/* the other synthetic families of SURVEY.md §8d, same generator:
+ *   LPS_GEN_DENSE       as lps_generate_dense (param = pos_permille)
+ *   LPS_GEN_UNBOUNDED   the dense LP with every c_j > 0 and column `param` of A negated (no positive
+ *                       entry): unbounded, reported when that column enters (immediately for param = 0)
+ *   LPS_GEN_ASSIGNMENT  degenerate: 0/1 incidence matrix of a bipartite graph, b = 1, c = 1; totally
+ *                       unimodular, so every entry stays in {-1,0,1} (exact in binary64 and in the
+ *                       reference's decimal arithmetic) and zero-ratio ties abound */
+typedef enum { LPS_GEN_DENSE = 0, LPS_GEN_UNBOUNDED = 1, LPS_GEN_ASSIGNMENT = 2 } lps_gen_kind;
+int lps_generate_lp(lps_handle h, int kind, int m, int n, uint64_t seed, int param);
 
 /* LPState.getEntering() — LPState.java:274-285.  *e = -1 when no c[i] > epsilon. */
 int lps_get_entering(lps_handle h, int *e);
@@ -159,6 +168,8 @@ int lps_rebuild_objective(lps_handle h, const lps_objective_op *ops, int nops);
  * same max_pivots.  Field reads return the LOCAL rows; positions and the pivot log are global. */
 int lps_shard_generate_dense(lps_handle h, int m_total, int n, int rank, int world, uint64_t seed,
                              int pos_permille);
+int lps_shard_generate_lp(lps_handle h, int kind, int m_total, int n, int rank, int world, uint64_t seed,
+                          int param);
 int lps_shard_load(lps_handle h, int m_total, int n, int rank, int world, const double *A_local,
                    int64_t lda, const double *b_local, const double *c, double v);
 int lps_shard_info(lps_handle h, int *rank, int *world, int *m_total, int *row0, int *row1);

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "liblps_b200.so")
 LPS_OK = 0
 LPS_ERR_INVALID, LPS_ERR_CUDA, LPS_ERR_STATE, LPS_ERR_NOMEM, LPS_ERR_NODEVICE, LPS_ERR_COMM = -1, -2, -3, -4, -5, -6
 LPS_RUNNING, LPS_OPTIMAL, LPS_UNBOUNDED, LPS_PIVOT_CAP = 0, 1, 2, 3
+LPS_GEN_DENSE, LPS_GEN_UNBOUNDED, LPS_GEN_ASSIGNMENT = 0, 1, 2
 (LPSOLVER_OPTIMAL, LPSOLVER_UNBOUNDED, LPSOLVER_INFEASIBLE, LPSOLVER_AUX_UNBOUNDED,
  LPSOLVER_DEGENERATE_FAIL, LPSOLVER_INDEX_ERROR, LPSOLVER_PIVOT_CAP, LPSOLVER_ERROR) = range(8)
 
@@ -59,6 +60,7 @@ SIGNATURES = {
     "lps_load": (c_int, [c_void_p, c_int, c_int, _dp, c_int64, _dp, _dp, c_double]),
     "lps_load_aux": (c_int, [c_void_p, c_int, c_int, _dp, c_int64, _dp]),
     "lps_generate_dense": (c_int, [c_void_p, c_int, c_int, c_uint64, c_int]),
+    "lps_generate_lp": (c_int, [c_void_p, c_int, c_int, c_int, c_uint64, c_int]),
     "lps_get_entering": (c_int, [c_void_p, _ip]),
     "lps_get_leaving": (c_int, [c_void_p, c_int, _ip]),
     "lps_pivot": (c_int, [c_void_p, c_int, c_int]),
@@ -81,6 +83,7 @@ SIGNATURES = {
     "lps_tableau_bytes": (c_int, [c_void_p, POINTER(c_int64)]),
     "lps_algorithmic_bytes_per_pivot": (c_int, [c_void_p, POINTER(c_int64)]),
     "lps_shard_generate_dense": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_uint64, c_int]),
+    "lps_shard_generate_lp": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint64, c_int]),
     "lps_shard_load": (c_int, [c_void_p, c_int, c_int, c_int, c_int, _dp, c_int64, _dp, _dp, c_double]),
     "lps_shard_info": (c_int, [c_void_p, _ip, _ip, _ip, _ip, _ip]),
     "lps_shard_export": (c_int, [c_void_p, c_void_p]),

@@ -814,20 +814,27 @@ int lps_load_aux(lps_handle h, int m, int n, const double* A, int64_t lda, const
   return load_common(h, m, n, n + 1, A, lda, b, nullptr, 0.0, true);
 }
 
-int lps_generate_dense(lps_handle h, int m, int n, uint64_t seed, int pos_permille) {
-  if (!h || m <= 0 || n <= 0) return fail(h, LPS_ERR_INVALID, "lps_generate_dense: bad dimensions");
+int lps_generate_lp(lps_handle h, int kind, int m, int n, uint64_t seed, int param) {
+  if (!h || m <= 0 || n <= 0) return fail(h, LPS_ERR_INVALID, "lps_generate_lp: bad dimensions");
+  if (kind < 0 || kind > 2 || (kind == LPS_GEN_UNBOUNDED && (param < 0 || param >= n)) ||
+      (kind == LPS_GEN_ASSIGNMENT && m < 2))
+    return fail(h, LPS_ERR_INVALID, "lps_generate_lp: bad kind / parameter");
   CK(cudaSetDevice(h->dev));
   int rc = ensure_buffers(h, m, n);
   if (rc) return rc;
   rc = ensure_self_comm(h);
   if (rc) return rc;
   dim3 grid(std::min(cdiv(h->ld, 256), 64), std::min(m + 1, 65535));
-  k_generate_dense<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m, n, seed, pos_permille);
+  ks_generate_lp<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m, n, 0, m, seed, kind, param);
   CK(cudaGetLastError());
   rc = reset_state(h);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return LPS_OK;
+}
+
+int lps_generate_dense(lps_handle h, int m, int n, uint64_t seed, int pos_permille) {
+  return lps_generate_lp(h, LPS_GEN_DENSE, m, n, seed, pos_permille);
 }
 
 int lps_get_entering(lps_handle h, int* e) {
@@ -1237,19 +1244,27 @@ int lps_algorithmic_bytes_per_pivot(lps_handle h, int64_t* bytes) {
 }
 
 // ---- row-sharded API ------------------------------------------------------------------------
-int lps_shard_generate_dense(lps_handle h, int m_total, int n, int rank, int world, uint64_t seed,
-                             int pos_permille) {
-  if (!h || m_total <= 0 || n <= 0) return fail(h, LPS_ERR_INVALID, "lps_shard_generate_dense: bad dimensions");
+int lps_shard_generate_lp(lps_handle h, int kind, int m_total, int n, int rank, int world, uint64_t seed,
+                          int param) {
+  if (!h || m_total <= 0 || n <= 0) return fail(h, LPS_ERR_INVALID, "lps_shard_generate_lp: bad dimensions");
+  if (kind < 0 || kind > 2 || (kind == LPS_GEN_UNBOUNDED && (param < 0 || param >= n)) ||
+      (kind == LPS_GEN_ASSIGNMENT && m_total < 2))
+    return fail(h, LPS_ERR_INVALID, "lps_shard_generate_lp: bad kind / parameter");
   CK(cudaSetDevice(h->dev));
   int rc = shard_setup(h, m_total, n, rank, world);
   if (rc) return rc;
   dim3 grid(std::min(cdiv(h->ld, 256), 64), std::min(h->m + 1, 65535));
-  ks_generate_dense<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m_total, n, h->row0, h->row1, seed, pos_permille);
+  ks_generate_lp<<<grid, 256, 0, h->stream>>>(h->T, h->ld, m_total, n, h->row0, h->row1, seed, kind, param);
   CK(cudaGetLastError());
   rc = shard_reset_state(h);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return LPS_OK;
+}
+
+int lps_shard_generate_dense(lps_handle h, int m_total, int n, int rank, int world, uint64_t seed,
+                             int pos_permille) {
+  return lps_shard_generate_lp(h, LPS_GEN_DENSE, m_total, n, rank, world, seed, pos_permille);
 }
 
 int lps_shard_load(lps_handle h, int m_total, int n, int rank, int world, const double* A_local,

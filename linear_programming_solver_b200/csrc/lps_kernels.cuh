@@ -417,7 +417,7 @@ __global__ void k_rebuild_objective(double* T, long long ld, int m, int n,
 }
 
 // ---------------------------------------------------------------------------------------------
-// synthetic dense LP, bit-identical to oracle/tier_f.py:gen_dense_feasible
+// counter-based generator of the synthetic LPs (kernels in lps_sharded.cuh)
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ULL;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -427,29 +427,6 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 __device__ __forceinline__ double synth_u(unsigned long long seed, unsigned long long k) {
   unsigned long long h = splitmix64(seed ^ (k * 0x9E3779B97F4A7C15ULL));
   return (double)((h >> 44) + 1ULL) * (1.0 / 1048576.0);
-}
-
-__global__ void k_generate_dense(double* T, long long ld, int m, int n, unsigned long long seed,
-                                 int pos_permille) {
-  const unsigned long long mn = (unsigned long long)m * (unsigned long long)n;
-  for (int i = blockIdx.y; i <= m; i += gridDim.y) {
-    double* row = T + (long long)i * ld;
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ld;
-         j += (long long)gridDim.x * blockDim.x) {
-      double v = 0.0;
-      if (i < m) {
-        if (j < n) v = synth_u(seed, (unsigned long long)i * n + j);
-        else if (j == n) v = __dmul_rn((double)n / 4.0, __dadd_rn(1.0, synth_u(seed, mn + n + i)));
-      } else if (j < n) {
-        v = synth_u(seed, mn + j);
-        if (pos_permille < 1000) {
-          unsigned long long sel = splitmix64(seed ^ ~(unsigned long long)j) % 1000ULL;
-          if (sel >= (unsigned long long)pos_permille) v = -v;
-        }
-      }
-      row[j] = v;
-    }
-  }
 }
 
 }  // namespace lps

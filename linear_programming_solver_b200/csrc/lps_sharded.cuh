@@ -403,25 +403,52 @@ ks_update(const CtlS* __restrict__ ctl, double* __restrict__ T, long long ld, in
   }
 }
 
-// synthetic dense LP, rows [row0,row1) of the m x n instance + the replicated objective row
-__global__ void ks_generate_dense(double* T, long long ld, int m, int n, int row0, int row1,
-                                  unsigned long long seed, int pos_permille) {
+// synthetic LPs, rows [row0,row1) of the m x n instance + the replicated objective
+// row; bit-identical to the numpy restatements in oracle/tier_f.py.
+//   kGenDense       A_ij = u(i*n+j), b_i = (n/4)(1+u), c_j = +-u(mn+j) (positive for `param` per mille)
+//   kGenUnbounded   the dense LP with every c_j > 0 and column `param` of A negated: no positive entry
+//                   in that column, so the LP is unbounded and the loop says so when the column enters
+//   kGenAssignment  degenerate: 0/1 incidence matrix of a bipartite graph (L = m/2 left rows, the rest
+//                   right rows; column j joins left row j % L and right row L + (j % L + 7919 (j / L)) % R),
+//                   b = 1, c = 1.  Totally unimodular: every tableau entry stays in {-1,0,1}, exact in
+//                   binary64 and in the reference's decimal arithmetic, with many zero-ratio ties.
+enum GenKind : int { kGenDense = 0, kGenUnbounded = 1, kGenAssignment = 2 };
+
+__global__ void ks_generate_lp(double* T, long long ld, int m, int n, int row0, int row1,
+                               unsigned long long seed, int kind, int param) {
   const unsigned long long mn = (unsigned long long)m * (unsigned long long)n;
   const int mloc = row1 - row0;
+  const int L = m / 2, R = m - L;
   for (int il = blockIdx.y; il <= mloc; il += gridDim.y) {
     double* row = T + (long long)il * ld;
     const int i = row0 + il;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ld;
          j += (long long)gridDim.x * blockDim.x) {
       double v = 0.0;
-      if (il < mloc) {
-        if (j < n) v = synth_u(seed, (unsigned long long)i * n + j);
-        else if (j == n) v = __dmul_rn((double)n / 4.0, __dadd_rn(1.0, synth_u(seed, mn + n + i)));
+      if (kind == kGenAssignment) {
+        if (il < mloc) {
+          if (j < n) {
+            const int left = (int)(j % L);
+            const int right = L + (int)(((j % L) + 7919ll * (j / L)) % R);
+            v = (i == left || i == right) ? 1.0 : 0.0;
+          } else if (j == n) {
+            v = 1.0;
+          }
+        } else if (j < n) {
+          v = 1.0;
+        }
+      } else if (il < mloc) {
+        if (j < n) {
+          v = synth_u(seed, (unsigned long long)i * n + j);
+          if (kind == kGenUnbounded && j == param) v = -v;
+        } else if (j == n) {
+          v = __dmul_rn((double)n / 4.0, __dadd_rn(1.0, synth_u(seed, mn + n + i)));
+        }
       } else if (j < n) {
         v = synth_u(seed, mn + j);
-        if (pos_permille < 1000) {
+        if (kind == kGenDense && param < 1000) {
           unsigned long long sel = splitmix64(seed ^ ~(unsigned long long)j) % 1000ULL;
-          if (sel >= (unsigned long long)pos_permille) v = -v;
+          if (sel >= (unsigned long long)param) v = -v;
         }
       }
       row[j] = v;

@@ -68,6 +68,11 @@ class LPState:
 
     @classmethod
     def synthetic_dense(cls, m, n, seed=0, pos_permille=1000, **kw) -> "LPState":
+        return cls.synthetic(N.LPS_GEN_DENSE, m, n, seed, pos_permille, **kw)
+
+    @classmethod
+    def synthetic(cls, kind, m, n, seed=0, param=1000, **kw) -> "LPState":
+        """One of the synthetic families of SURVEY.md §8d, generated in HBM (lps_generate_lp)."""
         st = cls.__new__(cls)
         st._lib = N.load()
         st._h = c_void_p()
@@ -83,7 +88,7 @@ class LPState:
         rc = st._lib.lps_create(byref(st._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + st._lib.lps_status_string(rc).decode())
-        st._ck(st._lib.lps_generate_dense(st._h, m, n, seed, pos_permille), "lps_generate_dense")
+        st._ck(st._lib.lps_generate_lp(st._h, int(kind), m, n, seed, int(param)), "lps_generate_lp")
         return st
 
     def _ck(self, rc, what):

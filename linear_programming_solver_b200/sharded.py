@@ -51,7 +51,8 @@ class ShardedLPState(LPState):
     def __init__(self, m_total: int, n: int, rank: int, world: int, A_local=None, b_local=None, c=None,
                  v: float = 0.0, synthetic_seed: Optional[int] = None, pos_permille: int = 1000,
                  epsilon: float = LPState.DEF_EPSILON, inf: float = LPState.DEF_INF, device: int = -1,
-                 time_kernels: bool = False, loop_mode: int = 0, block_pivots: int = 0):
+                 time_kernels: bool = False, loop_mode: int = 0, block_pivots: int = 0,
+                 synthetic_kind: int = N.LPS_GEN_DENSE):
         self._lib = N.load()
         self._h = c_void_p()
         self._names0 = None
@@ -65,8 +66,8 @@ class ShardedLPState(LPState):
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + self._lib.lps_status_string(rc).decode())
         if synthetic_seed is not None:
-            self._ck(self._lib.lps_shard_generate_dense(self._h, m_total, n, rank, world, synthetic_seed,
-                                                        pos_permille), "lps_shard_generate_dense")
+            self._ck(self._lib.lps_shard_generate_lp(self._h, int(synthetic_kind), m_total, n, rank, world,
+                                                     synthetic_seed, pos_permille), "lps_shard_generate_lp")
         else:
             mloc = self.row1 - self.row0
             A_local = np.ascontiguousarray(np.asarray(A_local, dtype=np.float64).reshape(mloc, n))

@@ -260,6 +260,29 @@ def gen_dense_feasible(m: int, n: int, seed: int = 0, pos_permille: int = 1000, 
     return A, b, c
 
 
+def gen_unbounded(m: int, n: int, seed: int = 0, col: int = 0):
+    """C5 (iii) family: the dense LP with every c_j > 0 and column `col` of A negated — no positive
+    entry in that column, so the LP is unbounded and the loop reports it when the column enters
+    (immediately for col = 0, after a long run for col = n-1)."""
+    A, b, c = gen_dense_feasible(m, n, seed, 1000)
+    A[:, col] = -A[:, col]
+    return A, b, c
+
+
+def gen_assignment(m: int, n: int):
+    """C5 (ii) family, degenerate: 0/1 incidence matrix of a bipartite graph (L = m//2 left rows, the
+    rest right rows; column j joins left row j % L and right row L + (j % L + 7919 (j // L)) % R),
+    b = 1, c = 1.  Totally unimodular: every tableau entry stays in {-1,0,1} (exact in binary64 AND in
+    the decimal-15 arithmetic of the reference), with many zero-ratio ties."""
+    L = m // 2
+    R = m - L
+    A = np.zeros((m, n), dtype=np.float64)
+    j = np.arange(n, dtype=np.int64)
+    A[j % L, j] = 1.0
+    A[L + ((j % L) + 7919 * (j // L)) % R, j] = 1.0
+    return A, np.ones(m), np.ones(n)
+
+
 def gen_mixed_rows(m: int, n: int, seed: int = 0, with_equalities: bool = True, frac_bits: int = 10):
     """C3 family: max c.x over rows lowered the way LPInputReader lowers them
     (LPInputReader.java:189-212), with a planted interior point x* = u(.) so the LP is feasible

@@ -1,0 +1,61 @@
+"""The blocked loop's algorithm (lazy replay of pending pivots + one pass per block), restated on
+the CPU in oracle/blocked_model.py, against the binary64 oracle: same pivot sequence, same verdict,
+every tableau cell bit-identical, for every block size.  This is the CPU-side proof of the claim
+the CUDA kernels in csrc/lps_blocked.cuh rely on (the GPU side of it is tests/test_gpu_blocked.py)."""
+import numpy as np
+import pytest
+
+from oracle import tier_f
+from oracle.blocked_model import OPTIMAL, PIVOT_CAP, UNBOUNDED, BlockedModel
+
+STATUS = {tier_f.OPTIMAL: OPTIMAL, tier_f.UNBOUNDED: UNBOUNDED, tier_f.PIVOT_CAP: PIVOT_CAP}
+
+
+def _check(A, b, c, block, cap=-1):
+    ref = tier_f.TierFState(A.copy(), b.copy(), c.copy())
+    status, k = ref.run(cap)
+    mdl = BlockedModel(A, b, c, block=block)
+    got, kk = mdl.run(cap)
+    assert got == STATUS[status] and kk == k
+    assert mdl.log == ref.log
+    assert np.array_equal(mdl.A, ref.A) and np.array_equal(mdl.b, ref.b) and np.array_equal(mdl.c, ref.c)
+    assert mdl.v == ref.v[0]
+    return mdl
+
+
+@pytest.mark.parametrize("block", [1, 2, 5, 16, 20])
+@pytest.mark.parametrize("m,n,seed", [(5, 7, 0), (12, 9, 1), (40, 80, 3), (100, 60, 4)])
+def test_blocked_model_equals_tier_f(m, n, seed, block):
+    A, b, c = tier_f.gen_dense_feasible(m, n, seed)
+    mdl = _check(A, b, c, block)
+    assert mdl.passes == -(-len(mdl.log) // block)     # one pass per block, ceil
+
+
+def test_blocked_model_cap_and_unbounded():
+    A, b, c = tier_f.gen_dense_feasible(30, 50, 2)
+    _check(A, b, c, 7, cap=23)
+    A2 = A.copy()
+    A2[:, 49] = -A2[:, 49]
+    _check(A2, b, c, 6)
+    A3 = A.copy()
+    A3[:, 0] = -A3[:, 0]
+    _check(A3, b, c, 6)
+
+
+def test_blocked_model_degenerate_rows_and_columns_repeat_inside_a_block():
+    k = 6
+    m, n = 2 * k, k * k
+    A = np.zeros((m, n))
+    for i in range(k):
+        for j in range(k):
+            A[i, i * k + j] = 1.0
+            A[k + j, i * k + j] = 1.0
+    b = np.ones(m)
+    c = np.random.default_rng(3).integers(1, 6, size=n).astype(np.float64)
+    for block in (3, 16):
+        mdl = _check(A, b, c, block, cap=2000)
+        # the point of the case: inside one block, some row or column is pivoted on more than once
+        rows = [l for _, l in mdl.log]
+        cols = [e for e, _ in mdl.log]
+        assert any(len(set(rows[s:s + block])) < len(rows[s:s + block]) or
+                   len(set(cols[s:s + block])) < len(cols[s:s + block]) for s in range(0, len(rows), block))
