@@ -107,7 +107,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.samples, self.proc, self.index = [], None, index
+        self.samples, self.proc, self.index, self.first = [], None, index, 0
 
     def start(self):
         try:
@@ -123,6 +123,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
+    def mark(self):
+        """the timed region starts here: earlier samples (warm-up) are dropped unless nothing else arrives"""
+        self.first = len(self.samples)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -133,7 +137,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        timed = self.samples[self.first:]
+        note = "sampled during the timed region"
+        if len(timed) < 2:                       # a very short timed region: fall back to the warm-up steps too
+            timed, note = self.samples, "timed region shorter than the sampling period: warm-up samples included"
+        for s in timed:
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 7:
                 continue
@@ -147,7 +155,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "note": note}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -233,11 +241,14 @@ def run_ours(args):
     def barrier():
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        st.run(P)
+    # nvidia-smi needs about a second to start answering: launch it before the warm-up and mark where
+    # the timed region begins, so that short timed regions still get their samples
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(args.warmup):
+        st.run(P)
     barrier()
+    sampler.mark()
     dev_ms, upd_ms, upd_n, launches, pivots = 0.0, 0.0, 0, 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):

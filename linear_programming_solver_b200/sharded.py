@@ -150,11 +150,12 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
         torch.cuda.synchronize()
         dist.barrier()
 
+    sampler = ClockSampler(local_rank)     # started before the warm-up: nvidia-smi takes a second to answer
+    sampler.start()
     for _ in range(args.warmup):
         st.run(P)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark()
     dev_ms, upd_ms, upd_n, launches, pivots = 0.0, 0.0, 0, 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):

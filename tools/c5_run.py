@@ -2,7 +2,7 @@
 box — the generic dense instance (capped), the degenerate assignment instance (full solve) and the
 unbounded instances (immediate, and after a long run).  Run under torchrun, one rank per GPU:
 
-    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/c5_run.py [--m 60000 --n 120000]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/c5_run.py [--rows 60000 --cols 120000]
 
 At this size nothing on the CPU can check the cells, so the checks are size-independent properties:
   * the pivot log of the sharded run equals, pivot for pivot, the log of the same LP on ONE GPU
@@ -35,8 +35,8 @@ def log_hash(log):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--m", type=int, default=60000)
-    ap.add_argument("--n", type=int, default=120000)
+    ap.add_argument("--rows", type=int, default=60000)
+    ap.add_argument("--cols", type=int, default=120000)
     ap.add_argument("--dense-pivots", type=int, default=2048)
     ap.add_argument("--check-pivots", type=int, default=256)
     ap.add_argument("--long-cap", type=int, default=40000)
@@ -46,7 +46,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    m, n = a.m, a.n
+    m, n = a.rows, a.cols
     out = {"m": m, "n": n, "world": world, "tableau_gb": 8.0 * (m + 1) * (n + 1) / 1e9, "cases": {}}
 
     def sharded(kind, param, seed=0):
