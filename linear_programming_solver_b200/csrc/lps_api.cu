@@ -80,6 +80,7 @@ struct lps_handle_s {
   unsigned long long* pmins = nullptr;    // kb_panel: per-CTA minima
   unsigned int* psync = nullptr;          // kb_panel: ticket / go words of its two grid-wide syncs
   unsigned int panel_launches = 0;        // tag source: never reset, so a stale slot can never match
+  bool panel_dirty = false;               // a run was abandoned inside a grid sync: re-arm the sync words
 
   std::vector<cudaEvent_t> ev;  // time_kernels event pool
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -551,6 +552,10 @@ int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   const int S = h->block;
   const bool panel_kernel = use_panel_kernel(h);
   long long launches = 0;
+  if (h->panel_dirty && h->psync) {
+    CK(cudaMemsetAsync(h->psync, 0, 1024, h->stream));
+    h->panel_dirty = false;
+  }
   CK(cudaEventRecord(h->ev_begin, h->stream));
   // the tableau is fully applied between calls, so the entering column comes from its objective row
   ks_begin_run<<<1, 1, 0, h->stream>>>(h->ctls, max_pivots, 1);
@@ -614,7 +619,10 @@ int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
     if (remaining >= 0) remaining -= done_now;
     if (h->h_ctl->status != kRunning) break;
   }
-  if (h->h_ctl->status == kCommTimeout) return fail(h, LPS_ERR_COMM, "shard: timed out waiting for a peer rank");
+  if (h->h_ctl->status == kCommTimeout) {
+    h->panel_dirty = true;
+    return fail(h, LPS_ERR_COMM, "shard: timed out waiting for a peer rank");
+  }
   if (h->h_ctls->blk_pending != 0) return fail(h, LPS_ERR_STATE, "blocked loop: pivots left pending after the last pass");
   CK(cudaEventRecord(h->ev_end, h->stream));
   CK(cudaEventSynchronize(h->ev_end));
@@ -627,21 +635,6 @@ int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
                  "commit %llu  (pivots %lld)  SM clock during the panel kernels: %.0f MHz\n",
                  d[6], d[7], d[8], d[0], d[1], d[2], d[9], d[10], d[11], d[3], d[4], d[5], (long long)h->total_pivots,
                  d[13] ? 1e3 * (double)d[12] / (double)d[13] : 0.0);
-    if (h->pmins && h->panel_grid > 0) {
-      std::vector<unsigned long long> m((size_t)h->panel_grid * 16);
-      cudaMemcpy(m.data(), h->pmins, m.size() * 8, cudaMemcpyDeviceToHost);
-      // event times of the last pivot, relative to the earliest A-start: min / median / max over CTAs
-      const char* names[6] = {"A start", "A publish", "gather A done", "B start", "B publish", "gather B done"};
-      unsigned long long t0 = ~0ull;
-      for (int c = 0; c < h->panel_grid; c++) t0 = std::min(t0, m[(size_t)c * 16 + 1]);
-      for (int q = 0; q < 6; q++) {
-        std::vector<long long> v;
-        for (int c = 0; c < h->panel_grid; c++) v.push_back((long long)(m[(size_t)c * 16 + 1 + q] - t0));
-        std::sort(v.begin(), v.end());
-        std::fprintf(stderr, "  %-14s min %6lld  med %6lld  max %6lld ns\n", names[q], v.front(), v[v.size() / 2], v.back());
-      }
-      std::fprintf(stderr, "\n");
-    }
   }
 #endif
   // the pivot-per-pass staging vectors (colbuf, bcol) are not maintained by this loop

@@ -405,9 +405,6 @@ constexpr unsigned long long kPanelSpinNs = 20ull * 1000ull * 1000ull * 1000ull;
   } while (0)
 #define PANEL_DUMP()                                         \
   do {                                                       \
-    if (tid == 0) {                                          \
-      _Pragma("unroll") for (int q_ = 0; q_ < 6; q_++) a.mins[cta * kMinStride + 1 + q_] = ev_[q_]; \
-    }                                                        \
     if (cta == 0 && tid == 0) {                              \
       _Pragma("unroll") for (int q_ = 0; q_ < 12; q_++) ctl->dbg_ns[q_] += dbg_[q_]; \
       ctl->dbg_ns[12] += (unsigned long long)(clock64() - clk0_);                      \
@@ -500,16 +497,12 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
   unsigned long long mark_ = globaltimer_ns();
   const long long clk0_ = clock64();
   const unsigned long long ns0_ = mark_;
-  unsigned long long ev_[6] = {0, 0, 0, 0, 0, 0};
 #endif
 
   while (t < a.block) {
     const unsigned int seq = (unsigned int)(np + 1);
     const int par = seq & 1;
     // ---------------- phase A: entering column, b column, ratio test ----------------
-#ifdef LPS_PANEL_TIMING
-    if (tid == 0) ev_[0] = globaltimer_ns();
-#endif
     PeerCand best;
     best.slack = a.inf; best.row = kNone; best.p = 0.0;
     if (e != kNone) {
@@ -572,9 +565,6 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
       mine->slack = c.slack;
       mine->p = c.p;
       mine->row = c.row;
-#ifdef LPS_PANEL_TIMING
-      ev_[1] = globaltimer_ns();
-#endif
     }
     PANEL_MARK(0);
     // all-gather of the partials: grid-wide arrive-and-wait, then thread k takes CTA k's slot
@@ -608,9 +598,6 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
       __syncthreads();
     }
     PANEL_MARK(1);
-#ifdef LPS_PANEL_TIMING
-    if (tid == 0) ev_[2] = globaltimer_ns();
-#endif
     if (warp == 0) {
       PeerCand c;
       c.slack = a.inf; c.row = kNone; c.p = 0.0;
@@ -711,9 +698,6 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
     // ---------------- phase B: leaving row, objective row, next entering column ----------------
     const bool i_own = !kSharded || (l >= a.row0 && l < a.row1);
     const int lloc = i_own ? l - a.row0 : -1;
-#ifdef LPS_PANEL_TIMING
-    if (tid == 0) ev_[3] = globaltimer_ns();
-#endif
     if (tid < t) {
       s_al[tid] = i_own ? ldcg_f64(a.Acols + (long long)tid * a.apitch + lloc) : 0.0;
       s_am[tid] = ldcg_f64(a.Acols + (long long)tid * a.apitch + mloc);
@@ -788,9 +772,6 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
       int v = s_min[0];
       for (int w = 1; w < kPanelThreads / 32; w++) v = min(v, s_min[w]);
       a.mins[cta * kMinStride] = (unsigned long long)(unsigned int)v;
-#ifdef LPS_PANEL_TIMING
-      ev_[4] = globaltimer_ns();
-#endif
     }
     PANEL_MARK(3);
     // all-gather of the per-CTA minima -> the next entering column (LPState.java:274-285)
@@ -820,9 +801,6 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
       __syncthreads();
     }
     PANEL_MARK(4);
-#ifdef LPS_PANEL_TIMING
-    if (tid == 0) ev_[5] = globaltimer_ns();
-#endif
     const int e2 = s_e2;
     if (cta == scribe && tid == 0) {                       // commit pivot(e, l)
       ctl->base.e_cur = e;
@@ -881,7 +859,7 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
   double* const s_a = smem + (size_t)2 * t * kStripCols;         // [2][t][kCH]
   __shared__ double s_p[kMaxBlock];
   __shared__ int s_l[kMaxBlock], s_e[kMaxBlock];
-  __shared__ long long s_claim[2], s_first[3];
+  __shared__ long long s_claim[2];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid / kFlushThreads, ltid = tid % kFlushThreads;
   if (tid < t) {
@@ -893,13 +871,12 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
   const int nrb = (mloc + 1 + kCH - 1) / kCH;                    // chunks per strip
   const long long nchunks = (long long)nstrips * nrb;
   unsigned long long* const queue = &ctl->blk_queue;
-  if (tid == 0) {
-    s_first[0] = (long long)atomicAdd(queue, 1ull);
-    s_first[1] = (long long)atomicAdd(queue, 1ull);
-    s_first[2] = (long long)atomicAdd(queue, 1ull);
-  }
+  // a CTA holds the chunk it is replaying and ONE more (whose operand slices are in flight): claiming
+  // further ahead leaves the last CTAs with a private backlog while the others idle, which at a few
+  // chunks per CTA (8-way shards, 10,000 x 10,000) was more than half of the kernel
+  if (tid == 0) s_claim[0] = (long long)atomicAdd(queue, 1ull);
   __syncthreads();
-  long long cur = s_first[0], nxt = s_first[1], nn = s_first[2];
+  long long cur = s_claim[0], nxt = 0;
 
   // chunk c's operand slices -> buffer `buf`
   auto prefetch = [&](long long c, int buf) {
@@ -923,14 +900,12 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
 
   if (cur < nchunks) prefetch(cur, 0);
   int buf = 0;
-  bool first = true;
   while (cur < nchunks) {
+    if (tid == 0) s_claim[buf ^ 1] = (long long)atomicAdd(queue, 1ull);   // the chunk after this one
     cp_async_wait_all();
     __syncthreads();   // this chunk's operands have landed; everyone is done with the other buffer
-    if (!first) nn = s_claim[buf ^ 1];
-    first = false;
+    nxt = s_claim[buf ^ 1];
     if (nxt < nchunks) prefetch(nxt, buf ^ 1);
-    if (tid == 0) s_claim[buf] = (long long)atomicAdd(queue, 1ull);   // read after the next barrier
 
     const long long j0 = (cur % nstrips) * kStripCols + 4 * ltid;
     {
@@ -1036,7 +1011,6 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
       }
     }
     cur = nxt;
-    nxt = nn;
     buf ^= 1;
   }
   // last CTA of the grid retires the block
