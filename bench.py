@@ -225,6 +225,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        # keep stdout to the one JSON line: NCCL's banner ("NCCL version ...") goes there at VERSION level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world > 1:
         from linear_programming_solver_b200 import sharded
