@@ -81,6 +81,7 @@ struct lps_handle_s {
   unsigned int* psync = nullptr;          // kb_panel: ticket / go words of its two grid-wide syncs
   unsigned int panel_launches = 0;        // tag source: never reset, so a stale slot can never match
   bool panel_dirty = false;               // a run was abandoned inside a grid sync: re-arm the sync words
+  long long ll_off = 0;                   // byte offset of the packet area inside the exchange block
 
   std::vector<cudaEvent_t> ev;  // time_kernels event pool
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -259,7 +260,10 @@ int prepare_next(lps_handle h) {
 // ---- row-sharded mode ---------------------------------------------------------------------
 int ensure_comm(lps_handle h) {
   // pivot-row store: 2 parity slots for the pivot-per-pass kernels, `block` slots for the blocked loop
-  size_t need = sizeof(CommBlock) + (size_t)std::max(2, h->block) * (size_t)h->ld * sizeof(double);
+  // ... then the packet area of kb_panel's exchange: LLPacket row[2][ld], LLPacket cand[2][kMaxRanks][4].
+  // Every rank of a sharded solve must be created with the same block_pivots: the offsets are shared.
+  h->ll_off = (long long)round_up((long long)(sizeof(CommBlock) + (size_t)std::max(2, h->block) * (size_t)h->ld * sizeof(double)), 16);
+  size_t need = (size_t)h->ll_off + (2 * (size_t)h->ld + 2 * kMaxRanks * 4) * sizeof(LLPacket);
   if (need > h->comm_bytes) {
     if (h->attached) return fail(h, LPS_ERR_STATE, "shard: tableau grew after peers were attached");
     if (h->comm) cudaFree(h->comm);
@@ -520,6 +524,7 @@ int launch_panel(lps_handle h) {
   pa.mins = h->pmins;
   pa.syncw = h->psync;
   pa.gwin = reinterpret_cast<PeerCand*>(h->psync + 192);   // its own 128-byte line behind the five sync words
+  pa.ll_off = h->ll_off;
   // 64 tags per launch (two per pivot, at most 32 pivots); tag 0 is the cleared state
   h->panel_launches += 1;
   pa.tag0 = h->panel_launches * 64u;

@@ -343,6 +343,38 @@ constexpr int kPanelThreads = 384;
 constexpr int kSlotStride = 128 / sizeof(PeerCand);             // slots are polled by every CTA: one L2 line each
 constexpr int kMinStride = 128 / sizeof(unsigned long long);
 
+// Flag-in-data packets for the cross-rank exchange of kb_panel: a double travels as one 16-byte store
+// {lo32, tag, hi32, tag}.  Each 8-byte half carries the tag, so only 8-byte store atomicity is assumed;
+// the receiver polls the packet itself until both tags match.  No flag word, no system-scope fence:
+// an exchange costs one NVLink traversal.  Tags are pivot numbers (never 0, the cleared state); slots
+// are double-buffered by pivot parity, so a stale packet carries tag - 2.
+struct __align__(16) LLPacket {
+  unsigned int lo, tag0, hi, tag1;
+};
+__device__ __forceinline__ void ll_store(LLPacket* dst, double v, unsigned int tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"((unsigned int)b), "r"(tag),
+               "r"((unsigned int)(b >> 32)), "r"(tag)
+               : "memory");
+}
+// false on timeout
+__device__ __forceinline__ bool ll_load(const LLPacket* src, unsigned int tag, double& v) {
+  unsigned int lo, t0, hi, t1;
+  unsigned int spins = 0;
+  unsigned long long start = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(src) : "memory");
+    if (t0 == tag && t1 == tag) break;
+    if ((++spins & 1023u) == 0) {
+      const unsigned long long now = globaltimer_ns();
+      if (start == 0) start = now;
+      else if (now - start > kSpinTimeoutNs) return false;
+    }
+  }
+  v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+  return true;
+}
+
 struct PanelArgs {
   CtlS* ctl;
   const double* T;
@@ -355,6 +387,8 @@ struct PanelArgs {
   unsigned long long* mins;        // [gridDim.x * kMinStride] first improving column of the CTA's range
   unsigned int* syncw;             // words on their own 128-byte lines: ticket A, go A, ticket B, go B, go W
   PeerCand* gwin;                  // sharded: the cross-rank winner, published by CTA 0 for the other CTAs
+  long long ll_off;                // sharded: byte offset, inside every rank's exchange block, of the packet
+                                   // area: LLPacket row[2][ld], then LLPacket cand[2][kMaxRanks][4]
   Peers peers;
   int rank, world;
   int2* plog;
@@ -468,7 +502,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
   __shared__ PeerCand s_red[kPanelThreads / 32], s_red2[kPanelThreads / 32];
   __shared__ int s_min[kPanelThreads / 32], s_min2[kPanelThreads / 32];
   __shared__ double s_slack, s_pw, s_ce;
-  __shared__ int s_row, s_ok, s_ok2, s_e2;
+  __shared__ int s_row, s_ok, s_e2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x, G = gridDim.x;
   const long long ld = a.ld;
@@ -614,21 +648,21 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
         // only CTA 0 talks to the peers (148 CTAs polling the same two mailbox lines would fight the
         // incoming NVLink writes); it hands the cross-rank winner to the other CTAs through one go word
         if (cta == 0) {
-          if (lane < a.world) {   // one lane per peer (own mailbox included)
-            PeerCand* dst = &a.peers.blk[lane]->cand[par][a.rank];
-            dst->slack = c.slack;
-            dst->p = c.p;
-            dst->row = (c.row == kNone) ? kNone : a.row0 + c.row;
-            st_release_sys(&dst->seq, seq);
+          if (lane < a.world) {   // one lane per peer (own packet slots included): three packets, no fence
+            LLPacket* dst = reinterpret_cast<LLPacket*>(reinterpret_cast<char*>(a.peers.blk[lane]) + a.ll_off) +
+                            2 * ld + ((size_t)par * kMaxRanks + a.rank) * 4;
+            ll_store(dst + 0, c.slack, seq);
+            ll_store(dst + 1, c.p, seq);
+            ll_store(dst + 2, (double)((c.row == kNone) ? -1 : a.row0 + c.row), seq);   // row < 2^31: exact
           }
           PeerCand pc;
           pc.slack = a.inf; pc.row = kNone; pc.p = 0.0;
           if (lane < a.world) {
-            const PeerCand* src = &a.peers.blk[a.rank]->cand[par][lane];
-            ok = spin_until<false>(&src->seq, seq) ? 1 : 0;
-            pc.slack = ld_volatile_f64(&src->slack);
-            pc.p = ld_volatile_f64(&src->p);
-            pc.row = ld_volatile_s32(&src->row);
+            const LLPacket* src = reinterpret_cast<const LLPacket*>(reinterpret_cast<const char*>(a.peers.blk[a.rank]) + a.ll_off) +
+                                  2 * ld + ((size_t)par * kMaxRanks + lane) * 4;
+            double rowd = -1.0;
+            ok = (ll_load(src + 0, seq, pc.slack) && ll_load(src + 1, seq, pc.p) && ll_load(src + 2, seq, rowd)) ? 1 : 0;
+            pc.row = (rowd < 0.0) ? kNone : (int)rowd;
           }
           ok = __all_sync(0xffffffffu, ok) ? 1 : 0;
 #pragma unroll
@@ -703,7 +737,6 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
       s_am[tid] = ldcg_f64(a.Acols + (long long)tid * a.apitch + mloc);
     }
     if (tid == kPanelThreads - 1) s_ce = ldcg_f64(a.Acols + (long long)t * a.apitch + mloc);
-    if (tid == 0) s_ok2 = (kSharded && !i_own) ? (spin_until<false>(&a.peers.blk[a.rank]->row_flag[par][cta], seq) ? 1 : 0) : 1;
     int mine_next = kNone;
     for (long long jb = jlo; jb < jhi; jb += kPanelThreads) {   // one trip unless ld > threads * gridDim.x
       const long long j = jb + tid;
@@ -716,16 +749,9 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
       }
       cp_async_commit();
       cp_async_wait_all();
-      __syncthreads();     // s_al / s_am / s_ce / s_ok2
+      __syncthreads();     // s_al / s_am / s_ce
       if (jb == jlo) PANEL_MARK(9);
-      if (kSharded && !s_ok2) {
-        if (tid == 0) {
-          ctl->base.status = kCommTimeout;
-          ctl->abort = 1;
-          __threadfence();
-        }
-        return;
-      }
+      bool got = true;
       if (j < jhi) {
         const double ce = s_ce;
         for (int u = 0; u < t; u++) {
@@ -739,26 +765,32 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
         double r = 0.0;
         if (i_own) {
           if (j <= n) r = ((int)j == e) ? ddiv_call(1.0, p) : ddiv_call(x, p);      // LPState.java:139-146
-          if (kSharded) {
-            for (int k = 0; k < a.world; k++) (a.peers.rowbuf[k] + (long long)t * ld)[j] = r;
-          } else {
-            (a.peers.rowbuf[0] + (long long)t * ld)[j] = r;
+          if (kSharded) {      // compute + broadcast in one kernel: one packet per peer, straight into its memory
+            for (int k = 0; k < a.world; k++)
+              if (k != a.rank)
+                ll_store(reinterpret_cast<LLPacket*>(reinterpret_cast<char*>(a.peers.blk[k]) + a.ll_off) +
+                             (size_t)par * ld + j, r, seq);
           }
         } else {
-          r = ld_volatile_f64(rows + (long long)t * ld + j);
+          got = ll_load(reinterpret_cast<const LLPacket*>(reinterpret_cast<const char*>(a.peers.blk[a.rank]) + a.ll_off) +
+                            (size_t)par * ld + j, seq, r);
         }
+        (a.peers.rowbuf[a.rank] + (long long)t * ld)[j] = r;     // this rank's copy of the pending row
         if (j < n) {
           double cn = ((int)j == e) ? -ddiv_call(ce, p) : __dsub_rn(xc, __dmul_rn(ce, r));   // :170-178
           if (cn > a.eps && (int)j < mine_next) mine_next = (int)j;
         }
       }
-      __syncthreads();     // s_op is reused by the next trip / phase A
+      if (__syncthreads_or(got ? 0 : 1)) {   // (also: s_op is reused by the next trip / phase A)
+        if (tid == 0) {        // the owner's packets never came
+          ctl->base.status = kCommTimeout;
+          ctl->abort = 1;
+          __threadfence();
+        }
+        return;
+      }
     }
     PANEL_MARK(10);
-    if (kSharded && i_own) {
-      __syncthreads();     // the CTA's stores into the peers' row stores, then one release per peer
-      if (tid < a.world && tid != a.rank) st_release_sys(&a.peers.blk[tid]->row_flag[par][cta], seq);
-    }
     mine_next = warp_min_int(mine_next);
     if (lane == 0) s_min[warp] = mine_next;
     if (tid == 0) {          // every CTA keeps its own copy of the pending pivots' scalars
