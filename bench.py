@@ -123,6 +123,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
+    def wait_first(self, timeout=10.0):
+        """block until nvidia-smi has answered once (it can take seconds on an 8-GPU box)"""
+        t0 = time.perf_counter()
+        while self.proc and not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
     def mark(self):
         """the timed region starts here: earlier samples (warm-up) are dropped unless nothing else arrives"""
         self.first = len(self.samples)
@@ -248,6 +254,7 @@ def run_ours(args):
     # the timed region begins, so that short timed regions still get their samples
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_first()
     for _ in range(args.warmup):
         st.run(P)
     barrier()

@@ -152,6 +152,8 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
 
     sampler = ClockSampler(local_rank)     # started before the warm-up: nvidia-smi takes a second to answer
     sampler.start()
+    if rank == 0:
+        sampler.wait_first()
     for _ in range(args.warmup):
         st.run(P)
     barrier()
