@@ -870,9 +870,8 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
 // and arrive by cp.async while the previous chunk is being computed:
 //   s_r [2][t][512]   the strip's slice of the pending rows
 //   s_a [2][t][kCH]   the chunk's slice of the pending columns
-// so the inner loop is LDS + DMUL/DADD only.  A group of rows that holds no pending pivot row, in a
-// thread that holds no pending pivot column, runs branch-free; anything else takes the generic
-// replay() path row by row.
+// so the inner loop is LDS + DMUL/DADD only, branch-free for every cell; the few cells a pending
+// pivot overwrites (its leaving row, its entering column) are recomputed afterwards.
 constexpr int kFlushThreads = 128;
 constexpr int kStripCols = 4 * kFlushThreads;
 
@@ -946,9 +945,22 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
       const int i_end = min(i0 + kCH, mloc + 1);
       const double* sr = s_r + (size_t)buf * t * kStripCols + 2 * ltid;
       const double* sa = s_a + (size_t)buf * t * kCH;
-      unsigned int cmask = 0;   // pending pivots whose entering column is one of my four
-      for (int u = 0; u < t; u++)
+      // Cells that a pending pivot OVERWRITES rather than updates are rare: a thread's four columns hold
+      // one of the t entering columns (cmask, per thread), or the chunk holds one of the t leaving rows
+      // (rmask, same for the whole CTA; only the last pivot on a row counts).  Everybody first runs the
+      // branch-free replay on every cell, then those cells are recomputed from the pivot that overwrote
+      // them — the same values, since nothing before an overwrite survives it — so a warp with a special
+      // column or row costs a few dozen instructions more instead of taking a branchy path for the
+      // whole group (which left its lane late at every chunk barrier).
+      unsigned int cmask = 0, rmask = 0;
+      for (int u = 0; u < t; u++) {
         if (s_e[u] >= j0 && s_e[u] < j0 + 4) cmask |= 1u << u;
+        if (s_l[u] >= i0 && s_l[u] < i_end) {
+          bool last = true;
+          for (int w = u + 1; w < t; w++) last &= (s_l[w] != s_l[u]);
+          if (last) rmask |= 1u << u;
+        }
+      }
       double* base = T + j0;
       auto rvec = [&](int u) {
         const double2 lo = *reinterpret_cast<const double2*>(sr + u * kStripCols);
@@ -961,23 +973,23 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
 #pragma unroll
         for (int k = 0; k < kU; k++)
           if (i + k < i_end) x[k] = ld256(base + (long long)(i + k) * ld);
+          else x[k].x = x[k].y = x[k].z = x[k].w = 0.0;
       };
       // replay the pending pivots on one group of rows held in registers, then store it
       auto finish_group = [&](D4 (&x)[kU], int i, int g) {
-        // a full group without a pending pivot row, in a thread without a pending pivot column?
-        bool plain = (cmask == 0) && (i + kU <= i_end);
-        for (int u = 0; u < t; u++) plain &= !(s_l[u] >= i && s_l[u] < i + kU);
-        if (plain) {
-#pragma unroll 2
-          for (int u = 0; u < t; u++) {
-            const D4 r = rvec(u);
-            double av[kU];
+        // 1. every pending pivot on every cell, branch-free; the operands of pivot u + 1 are fetched from
+        //    shared memory before the 8 kU FP64 instructions of pivot u are issued
+        {
+          auto load_ops = [&](int u, D4& r, double (&av)[kU]) {
+            r = rvec(u);
 #pragma unroll
             for (int q = 0; q < kU / 2; q++) {
               const double2 v = *reinterpret_cast<const double2*>(sa + u * kCH + g * kU + 2 * q);
               av[2 * q] = v.x;
               av[2 * q + 1] = v.y;
             }
+          };
+          auto apply = [&](const D4& r, const double (&av)[kU]) {
 #pragma unroll
             for (int k = 0; k < kU; k++) {
               x[k].x = __dsub_rn(x[k].x, __dmul_rn(av[k], r.x));
@@ -985,31 +997,64 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
               x[k].z = __dsub_rn(x[k].z, __dmul_rn(av[k], r.z));
               x[k].w = __dsub_rn(x[k].w, __dmul_rn(av[k], r.w));
             }
+          };
+          D4 r0, r1;
+          double a0[kU], a1[kU];
+          load_ops(0, r0, a0);
+          int u = 0;
+          for (; u + 2 <= t; u += 2) {
+            load_ops(u + 1, r1, a1);
+            apply(r0, a0);
+            if (u + 2 < t) load_ops(u + 2, r0, a0);
+            apply(r1, a1);
           }
+          if (u < t) apply(r0, a0);
+        }
+        // 2. my columns that were an entering column: -(a/p) at the last such pivot, plain updates after it
+        if (cmask != 0) {
 #pragma unroll
-          for (int k = 0; k < kU; k++) st256(base + (long long)(i + k) * ld, x[k]);
-        } else {
-          for (int u = 0; u < t; u++) {
-            const D4 r = rvec(u);
-            const int lu = s_l[u];
-            const int ce = ((cmask >> u) & 1u) ? (int)(s_e[u] - j0) : -1;
-            const double pu = s_p[u];
+          for (int c = 0; c < 4; c++) {      // c is a compile-time constant: x stays in registers
+            int us = -1;
+            for (int u = 0; u < t; u++)
+              if (((cmask >> u) & 1u) && s_e[u] - j0 == c) us = u;
+            if (us < 0) continue;
 #pragma unroll
             for (int k = 0; k < kU; k++) {
-              if (i + k < i_end) {
-                const double a = sa[u * kCH + g * kU + k];
-                const bool prow = (i + k == lu);
-                x[k].x = replay(x[k].x, prow, ce == 0, a, r.x, pu);
-                x[k].y = replay(x[k].y, prow, ce == 1, a, r.y, pu);
-                x[k].z = replay(x[k].z, prow, ce == 2, a, r.z, pu);
-                x[k].w = replay(x[k].w, prow, ce == 3, a, r.w, pu);
+              double y = -__ddiv_rn(sa[us * kCH + g * kU + k], s_p[us]);        // LPState.java:157 / :172
+              for (int u = us + 1; u < t; u++) {
+                const D4 r = rvec(u);
+                const double rc = (c == 0) ? r.x : (c == 1) ? r.y : (c == 2) ? r.z : r.w;
+                y = __dsub_rn(y, __dmul_rn(sa[u * kCH + g * kU + k], rc));
               }
+              if (c == 0) x[k].x = y; else if (c == 1) x[k].y = y; else if (c == 2) x[k].z = y; else x[k].w = y;
             }
           }
-#pragma unroll
-          for (int k = 0; k < kU; k++)
-            if (i + k < i_end) st256(base + (long long)(i + k) * ld, x[k]);
         }
+        // 3. rows of this group that were a leaving row: the scaled row of the last such pivot, then the
+        //    later pivots on it (a later entering column among my four overwrites again)
+        if (rmask != 0) {
+          for (int us = 0; us < t; us++) {
+            if (!((rmask >> us) & 1u) || s_l[us] < i || s_l[us] >= i + kU) continue;
+            const int ks = s_l[us] - i;
+            D4 y = rvec(us);                                                         // LPState.java:137-146
+            for (int u = us + 1; u < t; u++) {
+              const D4 r = rvec(u);
+              const double a = sa[u * kCH + g * kU + ks];
+              const int ce = ((cmask >> u) & 1u) ? (int)(s_e[u] - j0) : -1;
+              const double q = (ce >= 0) ? -__ddiv_rn(a, s_p[u]) : 0.0;
+              y.x = (ce == 0) ? q : __dsub_rn(y.x, __dmul_rn(a, r.x));
+              y.y = (ce == 1) ? q : __dsub_rn(y.y, __dmul_rn(a, r.y));
+              y.z = (ce == 2) ? q : __dsub_rn(y.z, __dmul_rn(a, r.z));
+              y.w = (ce == 3) ? q : __dsub_rn(y.w, __dmul_rn(a, r.w));
+            }
+#pragma unroll
+            for (int k = 0; k < kU; k++)
+              if (k == ks) x[k] = y;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kU; k++)
+          if (i + k < i_end) st256(base + (long long)(i + k) * ld, x[k]);
       };
       // the lane's NEXT group of rows (in this chunk, else the first one of the next chunk) is pulled
       // into L2 while this group is replayed: prefetches hold no register and no scoreboard
