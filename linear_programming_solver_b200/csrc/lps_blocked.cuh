@@ -335,10 +335,10 @@ kb_row(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
 // of a block (until the block is full, a verdict, or the pivot cap).  One CTA per SM; rows (phase
 // A) and columns (phase B) are dealt to CTAs statically, so a thread re-reads only pending-column
 // / pending-row entries its own CTA wrote.  The two global decisions of a pivot — the ratio-test
-// winner and the next entering column — are all-gathers through tagged slots: every CTA publishes
-// its partial result with a release store of a launch-unique tag and every CTA polls all the
-// slots, so a decision costs one L2 round trip after the slowest CTA instead of an atomic barrier
-// plus a reduction.  Values and decisions are the same as kb_col / kb_row, bit for bit.
+// winner and the next entering column — are all-gathers: every CTA writes its partial result into
+// its own slot, the grid meets in panel_sync (ticket + one go word), then thread k of every CTA
+// reads CTA k's slot and the CTA reduces the 148 values itself.  Values and decisions are the same
+// as kb_col / kb_row, bit for bit.
 constexpr int kPanelThreads = 384;
 constexpr int kSlotStride = 128 / sizeof(PeerCand);             // slots are polled by every CTA: one L2 line each
 constexpr int kMinStride = 128 / sizeof(unsigned long long);
@@ -383,7 +383,7 @@ struct PanelArgs {
   double* Acols;
   long long apitch;
   double eps, inf;
-  PeerCand* partials;              // [gridDim.x * kSlotStride] ratio-test partials, tagged, one 128-byte line each
+  PeerCand* partials;              // [gridDim.x * kSlotStride] ratio-test partials, one 128-byte line each
   unsigned long long* mins;        // [gridDim.x * kMinStride] first improving column of the CTA's range
   unsigned int* syncw;             // words on their own 128-byte lines: ticket A, go A, ticket B, go B, go W
   PeerCand* gwin;                  // sharded: the cross-rank winner, published by CTA 0 for the other CTAs
@@ -395,7 +395,7 @@ struct PanelArgs {
   long long log_cap;
   int* pos2var;
   int block;                       // pending pivots at which the launch stops (the pass comes next)
-  unsigned int tag0;               // launch-unique tag base: step s uses tag0 + 2s (+1 for phase B)
+  unsigned int tag0;               // launch-unique tag base: pivot s of the launch uses tag0 + s in both of its syncs
 };
 
 __device__ __forceinline__ double ldcg_f64(const double* p) {
@@ -865,7 +865,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
 // One persistent CTA per SM, kLanes x 128 threads.  Work is cut into chunks of kCH rows x 512
 // columns, numbered row-band-major (consecutive chunks are neighbouring strips of the same rows, so
 // the CTAs of the grid sweep the tableau as one band: DRAM pages stay open) and claimed from an
-// atomic counter two chunks ahead.  Each 128-thread lane owns whole groups of kU rows (kU 256-bit
+// atomic counter one chunk ahead.  Each 128-thread lane owns whole groups of kU rows (kU 256-bit
 // loads in flight per thread).  The operands of the replay are double-buffered in shared memory
 // and arrive by cp.async while the previous chunk is being computed:
 //   s_r [2][t][512]   the strip's slice of the pending rows
