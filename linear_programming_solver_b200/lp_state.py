@@ -89,7 +89,13 @@ class LPState:
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + st._lib.lps_status_string(rc).decode())
         st._ck(st._lib.lps_generate_lp(st._h, int(kind), m, n, seed, int(param)), "lps_generate_lp")
+        st._synthetic = (int(kind), m, n, seed, int(param))
         return st
+
+    def regenerate(self) -> None:
+        """Generate the same synthetic LP again on this handle (state, positions and log start over)."""
+        kind, m, n, seed, param = self._synthetic
+        self._ck(self._lib.lps_generate_lp(self._h, kind, m, n, seed, param), "lps_generate_lp")
 
     def _ck(self, rc, what):
         if rc == N.LPS_OK:
