@@ -137,3 +137,99 @@ class BlockedModel:
     @property
     def v(self):
         return 0.0 - self.T[self.m, self.n]
+
+
+class ShardedBlockedModel(BlockedModel):
+    """One rank of the row-sharded blocked loop (csrc/lps_blocked.cuh with world > 1): the rank holds
+    rows [lo, hi) of (A | b) plus a replica of the objective row, keeps ITS entries of the pending
+    columns and a full copy of the pending rows, and talks to the other ranks through two callbacks —
+    `all_gather(obj) -> list` for the ratio-test candidates and `broadcast(obj, src) -> obj` for the
+    scaled pivot row — which is exactly what crosses NVLink per pivot in the product."""
+
+    def __init__(self, A_local, b_local, c, lo, hi, m_total, owner_of, all_gather, broadcast, rank,
+                 v=0.0, block=16, eps=1e-9, inf=1e50):
+        super().__init__(A_local, b_local, c, v=v, block=block, eps=eps, inf=inf)
+        self.lo, self.hi, self.m_total = lo, hi, m_total
+        self.owner_of, self.all_gather, self.broadcast, self.rank = owner_of, all_gather, broadcast, rank
+
+    def run(self, max_pivots: int = -1):
+        m, n = self.m, self.n                     # m = local rows; local row m is the objective replica
+        done = 0
+        while True:
+            crow = self._row(m)
+            pos = np.nonzero(crow[:n] > self.eps)[0]
+            e = int(pos[0]) if pos.size else -1
+            best, l_loc = self.inf, -1
+            a = None
+            if e >= 0:
+                a = self._column(e)
+                bcol = self._column(n)
+                for i in range(m):
+                    if not (a[i] < self.eps):
+                        s = bcol[i] / a[i]
+                        if s < best:
+                            best, l_loc = s, i
+            cands = self.all_gather((float(best), self.lo + l_loc if l_loc >= 0 else -1,
+                                     float(a[l_loc]) if l_loc >= 0 else 0.0))
+            if e < 0:
+                self.flush()
+                return OPTIMAL, done
+            win = (self.inf, -1, 0.0)
+            for cand in cands:                    # lexicographic (ratio, global row): lowest row wins ties
+                if cand[1] >= 0 and (win[1] < 0 or cand[0] < win[0] or (cand[0] == win[0] and cand[1] < win[1])):
+                    win = cand
+            l, p = win[1], win[2]
+            if l < 0:
+                self.flush()
+                return UNBOUNDED, done
+            if 0 <= max_pivots <= done:
+                self.flush()
+                return PIVOT_CAP, done
+            owner = self.owner_of(l)
+            r = None
+            if owner == self.rank:                # compute + broadcast: the owner replays and scales row l
+                r = self._row(l - self.lo) / p
+                r[e] = 1.0 / p
+            r = self.broadcast(r, owner)
+            self.pend_e.append(e)
+            self.pend_l.append(l - self.lo if owner == self.rank else -1)
+            self.pend_p.append(p)
+            self.pend_a.append(a)
+            self.pend_r.append(np.asarray(r))
+            self.log.append((e, l))
+            done += 1
+            if len(self.pend_e) == self.block:
+                self.flush()
+
+    # a leaving row owned by another rank is "-1": it overwrites nothing here
+    def _column(self, j):
+        x = self.T[:, j].copy()
+        for e, l, p, a, r in zip(self.pend_e, self.pend_l, self.pend_p, self.pend_a, self.pend_r):
+            x = -(a / p) if j == e else x - a * r[j]
+            if l >= 0:
+                x[l] = r[j]
+        return x
+
+    def _row(self, i):
+        x = self.T[i, :].copy()
+        for e, l, p, a, r in zip(self.pend_e, self.pend_l, self.pend_p, self.pend_a, self.pend_r):
+            if l >= 0 and i == l:
+                x = r.copy()
+            else:
+                xe = -(a[i] / p)
+                x = x - a[i] * r
+                x[e] = xe
+        return x
+
+    def flush(self):
+        if not self.pend_e:
+            return
+        T = self.T
+        for e, l, p, a, r in zip(self.pend_e, self.pend_l, self.pend_p, self.pend_a, self.pend_r):
+            col_e = -(a / p)
+            T -= np.multiply.outer(a, r)
+            T[:, e] = col_e
+            if l >= 0:
+                T[l, :] = r
+        self.pend_e, self.pend_l, self.pend_p, self.pend_a, self.pend_r = [], [], [], [], []
+        self.passes += 1
