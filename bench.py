@@ -348,6 +348,17 @@ def run_ours(args):
             "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "first %d pivots of the same %dx%d LP in %.1f s, C binary64 twin of "
                       "LPState.pivotConcurrently with %d threads (reference THREAD_AMOUNT is 4)" % (k, m, n, dt, threads)}
+        # SURVEY 8d also asks for the reference's own thread count (THREAD_AMOUNT = 4, LPState.java:22);
+        # a short extra sample, never allowed to cost the line
+        try:
+            if threads > 4:
+                A_cpu[...] = A_host
+                rate4, k4, dt4 = cpu_port_rate(A_cpu, b_host.copy(), c_host.copy(), max(2, min(12, int(4.0 * rate))), 4)
+                line["cpu_baseline"]["value_4_threads"] = rate4
+                line["cpu_baseline"]["sample_4_threads"] = "first %d pivots in %.1f s with 4 threads" % (k4, dt4)
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline"]["value_4_threads"] = None
+            line["cpu_baseline"]["sample_4_threads"] = "failed: %s" % ex
     print(json.dumps(line), flush=True)
 
 
