@@ -59,3 +59,30 @@ def test_blocked_model_degenerate_rows_and_columns_repeat_inside_a_block():
         cols = [e for e, _ in mdl.log]
         assert any(len(set(rows[s:s + block])) < len(rows[s:s + block]) or
                    len(set(cols[s:s + block])) < len(cols[s:s + block]) for s in range(0, len(rows), block))
+
+
+# ---- property: any small LP, any block size ------------------------------------------------------
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=80, deadline=None)
+@given(m=st.integers(1, 9), n=st.integers(1, 9), block=st.integers(1, 20), seed=st.integers(0, 10 ** 6),
+       kind=st.sampled_from(["small_ints", "halves", "dense"]))
+def test_blocked_model_property(m, n, block, seed, kind):
+    """random tiny LPs with zeros, negative entries, ties, unbounded columns and repeated pivots on the
+    same row / column inside a block: the blocked replay and the pivot-per-pass oracle never differ"""
+    rng = np.random.default_rng(seed)
+    if kind == "small_ints":
+        A = rng.integers(-2, 4, size=(m, n)).astype(np.float64)
+        b = rng.integers(0, 5, size=m).astype(np.float64)          # zeros in b: degenerate ties
+        c = rng.integers(-2, 4, size=n).astype(np.float64)
+    elif kind == "halves":
+        A = rng.integers(-4, 9, size=(m, n)) / 2.0
+        b = rng.integers(0, 9, size=m) / 4.0
+        c = rng.integers(-4, 9, size=n) / 2.0
+    else:
+        A = rng.random((m, n)) - 0.2
+        b = rng.random(m)
+        c = rng.random(n) - 0.3
+    _check(A, b, c, block, cap=200)
