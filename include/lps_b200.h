@@ -61,7 +61,7 @@ typedef struct {
                            5 = blocked loop (block_pivots pivots per tableau pass) with two launches per
                            pivot, 6 = blocked loop with one cooperative launch per block */
   int block_pivots;     /* lps_run: pivots deferred between two passes over the tableau (blocked loop):
-                           0 = default (16), 1 = off (every pivot is its own pass), up to 32.  Values are
+                           0 = default (16), 1 = off (every pivot is its own pass), at most 20.  Values are
                            bit-identical for every setting. */
   int reserved[5];
 } lps_options;
