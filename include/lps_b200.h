@@ -59,11 +59,16 @@ typedef struct {
   int loop_mode;        /* lps_run: 0 = auto, 1 = three kernels per pivot, 2 = one persistent
                            cooperative kernel for the whole loop (grid barriers between phases),
                            5 = blocked loop (block_pivots pivots per tableau pass) with two launches per
-                           pivot, 6 = blocked loop with one cooperative launch per block */
+                           pivot, 6 = blocked loop with one cooperative panel launch per block followed by
+                           the pass, 7 = look-ahead blocked loop: ONE cooperative launch per block runs the
+                           pass of block k (out of place, TMA pipeline) and the panel of block k+1 side by
+                           side on disjoint SMs (needs a second tableau buffer; the default above 64 MB) */
   int block_pivots;     /* lps_run: pivots deferred between two passes over the tableau (blocked loop):
-                           0 = default (16), 1 = off (every pivot is its own pass), at most 20.  Values are
-                           bit-identical for every setting. */
-  int reserved[5];
+                           0 = default (16), 1 = off (every pivot is its own pass), at most 20 (16 for
+                           loop_mode 7).  Values are bit-identical for every setting. */
+  int panel_ctas;       /* loop_mode 7: CTAs (= SMs) given to the panel role, 0 = auto; the pass gets the rest */
+  int pass_chunk_rows;  /* TMA pass: rows per work chunk (rounded to a multiple of 12), 0 = auto */
+  int reserved[3];
 } lps_options;
 
 typedef struct {

@@ -25,7 +25,7 @@ LPS_GEN_DENSE, LPS_GEN_UNBOUNDED, LPS_GEN_ASSIGNMENT = 0, 1, 2
 class LpsOptions(Structure):
     _fields_ = [("epsilon", c_double), ("inf", c_double), ("device", c_int), ("time_kernels", c_int),
                 ("stream", c_void_p), ("update_variant", c_int), ("loop_mode", c_int), ("block_pivots", c_int),
-                ("reserved", c_int * 5)]
+                ("panel_ctas", c_int), ("pass_chunk_rows", c_int), ("reserved", c_int * 3)]
 
 
 class LpsRunResult(Structure):

@@ -15,6 +15,8 @@
 #include "lps_sharded.cuh"
 #include "lps_loop.cuh"
 #include "lps_blocked.cuh"
+#include "lps_sweep.cuh"
+#include "lps_step.cuh"
 
 using namespace lps;
 
@@ -82,6 +84,19 @@ struct lps_handle_s {
   unsigned int panel_launches = 0;        // tag source: never reset, so a stale slot can never match
   bool panel_dirty = false;               // a run was abandoned inside a grid sync: re-arm the sync words
   long long ll_off = 0;                   // byte offset of the packet area inside the exchange block
+
+  // TMA pass (lps_sweep.cuh) and look-ahead loop (lps_step.cuh)
+  double* T2 = nullptr;                   // second tableau buffer of the out-of-place pass (look-ahead loop only)
+  size_t T2_bytes = 0;
+  double *bvec = nullptr, *cvec = nullptr;   // running b column / objective row of the look-ahead panel
+  size_t bvec_cap = 0, cvec_cap = 0;
+  CUtensorMap tm_T[2];                    // tableau buffers (tm_T[1] == tm_T[0] when the pass runs in place)
+  CUtensorMap tm_A[2], tm_R[2];           // pending columns / rows of set 0 and 1
+  bool tm_valid = false;
+  int tm_rows_set = 0;                    // pending sets the maps were built for (1: in place, 2: look-ahead)
+  int step_grid = 0;                      // cooperative grid of kb_step (0 = not sized yet)
+  int sweep_grid = 0;                     // grid of the stand-alone kb_sweep (0 = not sized yet)
+  unsigned int look_launches = 0;         // launch counter of the look-ahead loop: parity + tag source
 
   std::vector<cudaEvent_t> ev;  // time_kernels event pool
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -155,9 +170,10 @@ int ensure_buffers(lps_handle h, int m, int n_cols /* n incl. any aux column */)
   h->m = m;
   h->n = n_cols;
   h->ld = ld;
+  h->tm_valid = false;   // tensor maps of the TMA pass describe the old buffers / shape
   if (h->block > 1) {
     h->apitch = round_up((long long)m + 1 + 512, 8);   // kb_flush copies whole chunks of rows
-    size_t aneed = (size_t)h->block * (size_t)h->apitch + 512;
+    size_t aneed = (size_t)2 * h->block * (size_t)h->apitch + 512;   // two pending sets (look-ahead loop)
     if (aneed > h->acols_cap) {
       if (h->acols) cudaFree(h->acols);
       h->acols = nullptr;
@@ -175,7 +191,16 @@ int ensure_comm(lps_handle h);
 // a single-GPU handle runs the blocked kernels as a world of one talking to itself
 int ensure_self_comm(lps_handle h) {
   if (h->block <= 1 || h->sharded) return LPS_OK;
-  if (h->ld > (long long)kMaxChunks * kChunk) return LPS_OK;   // too wide for the flag slots: unblocked
+  if (h->ld > (long long)kMaxChunks * kChunk) {   // too wide for the flag slots: unblocked
+    // a comm block left over from an earlier, narrower load would make use_blocked() say yes and the
+    // row kernels index their flag slots out of bounds
+    if (h->comm && !h->attached) {
+      cudaFree(h->comm);
+      h->comm = nullptr;
+      h->comm_bytes = 0;
+    }
+    return LPS_OK;
+  }
   h->rank = 0;
   h->world = 1;
   h->m_total = h->m;
@@ -245,8 +270,8 @@ int launch_ratio(lps_handle h, int mode) {
 int prepare_next(lps_handle h) {
   if (h->next_valid) return LPS_OK;
   k_begin_run<<<1, 1, 0, h->stream>>>(h->ctl, -1, 1);
-  k_first_positive<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->ctl, h->T + (long long)h->m * h->ld,
-                                                          h->n, h->opt.epsilon);
+  k_first_positive<<<std::max(1, cdiv(h->n, 256)), 256, 0, h->stream>>>(h->ctl, h->T + (long long)h->m * h->ld,
+                                                                       h->n, h->opt.epsilon);
   k_extract<<<cdiv(h->m + 1, 256), 256, 0, h->stream>>>(h->ctl, h->T, h->ld, h->m, h->n, -1, h->col0,
                                                        h->col1, h->bcol);
   CK(cudaGetLastError());
@@ -259,10 +284,10 @@ int prepare_next(lps_handle h) {
 
 // ---- row-sharded mode ---------------------------------------------------------------------
 int ensure_comm(lps_handle h) {
-  // pivot-row store: 2 parity slots for the pivot-per-pass kernels, `block` slots for the blocked loop
+  // pivot-row store: 2 parity slots for the pivot-per-pass kernels, 2 sets of `block` slots for the blocked loops
   // ... then the packet area of kb_panel's exchange: LLPacket row[2][ld], LLPacket cand[2][kMaxRanks][4].
   // Every rank of a sharded solve must be created with the same block_pivots: the offsets are shared.
-  h->ll_off = (long long)round_up((long long)(sizeof(CommBlock) + (size_t)std::max(2, h->block) * (size_t)h->ld * sizeof(double)), 16);
+  h->ll_off = (long long)round_up((long long)(sizeof(CommBlock) + (size_t)std::max(2, 2 * h->block) * (size_t)h->ld * sizeof(double)), 16);
   size_t need = (size_t)h->ll_off + (2 * (size_t)h->ld + 2 * kMaxRanks * 4) * sizeof(LLPacket);
   if (need > h->comm_bytes) {
     if (h->attached) return fail(h, LPS_ERR_STATE, "shard: tableau grew after peers were attached");
@@ -283,7 +308,9 @@ int ensure_comm(lps_handle h) {
 int shard_setup(lps_handle h, int m_total, int n, int rank, int world) {
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || m_total < 0 || n < 0)
     return fail(h, LPS_ERR_INVALID, "shard: bad rank/world/dimensions");
-  if ((long long)n + 1 > (long long)kMaxChunks * kChunk) return fail(h, LPS_ERR_INVALID, "shard: too many columns");
+  // row_flag has kMaxChunks slots per parity; the persistent loop uses one per kLoopChunk (128) columns
+  if ((long long)n + 1 > (long long)kMaxChunks * std::min(kChunk, kLoopChunk))
+    return fail(h, LPS_ERR_INVALID, "shard: too many columns");
   h->sharded = true;
   h->rank = rank;
   h->world = world;
@@ -318,8 +345,8 @@ int shard_reset_state(lps_handle h) {
 int shard_prepare_next(lps_handle h) {
   if (h->next_valid) return LPS_OK;
   ks_begin_run<<<1, 1, 0, h->stream>>>(h->ctls, -1, 1);
-  ks_first_positive<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->ctls, h->T + (long long)h->m * h->ld, h->n,
-                                                           h->opt.epsilon);
+  ks_first_positive<<<std::max(1, cdiv(h->n, 256)), 256, 0, h->stream>>>(h->ctls, h->T + (long long)h->m * h->ld, h->n,
+                                                                        h->opt.epsilon);
   ks_extract<<<cdiv(h->m + 1, 256), 256, 0, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->n, -1, h->col0,
                                                         h->col1, h->bcol);
   CK(cudaGetLastError());
@@ -435,15 +462,21 @@ bool use_blocked(lps_handle h) {
   return shard_bytes(h) > 64e6;
 }
 
+bool sweep_available(lps_handle h);
+int launch_sweep(lps_handle h);
+
 template <int kLanes, int kU, int kG, bool kPre>
 int launch_flush_t(lps_handle h) {
   constexpr int kCH = kU * kLanes * kG;
   const size_t smem = (size_t)h->block * 2 * (kStripCols + kCH) * sizeof(double);
   auto kern = kb_flush<kLanes, kU, kG, kPre>;
-  if (h->flush_grid == 0) {
+  // the shared-memory opt-in belongs to THIS instantiation (and device): a handle reloaded with an LP of another
+  // size can land on another instantiation, so the (cheap) attribute call is made at every launch
+  {
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int nb = 0;
-    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kFlushThreads * kLanes, smem);
+    int nb = 1;
+    if (ce == cudaSuccess && h->flush_grid == 0)
+      ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kFlushThreads * kLanes, smem);
     if (ce != cudaSuccess || nb < 1) {
       cudaGetLastError();
       return fail(h, LPS_ERR_STATE, "kb_flush does not fit on an SM with this block_pivots");
@@ -456,7 +489,9 @@ int launch_flush_t(lps_handle h) {
 }
 
 int launch_flush(lps_handle h) {
-  // <128-thread row-group lanes per CTA, rows per group, groups per lane per chunk, L2 prefetch of the next group>
+  // default (and update_variant >= 10): the TMA pipeline of lps_sweep.cuh, in place; update_variant 0..9 select the cp.async kernel
+  // kb_flush<128-thread row-group lanes per CTA, rows per group, groups per lane per chunk, L2 prefetch of the next group>
+  if ((h->opt.update_variant < 0 || h->opt.update_variant >= 10) && sweep_available(h)) return launch_sweep(h);
   switch (h->opt.update_variant) {
     default: {
       // chunk height: 256 rows is the best of the B200 sweep (profiles/) while every CTA still gets a
@@ -492,7 +527,9 @@ bool use_panel_kernel(lps_handle h) {
     if (ce == cudaSuccess)
       ce = h->sharded ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kb_panel<true>, kPanelThreads, smem)
                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kb_panel<false>, kPanelThreads, smem);
-    if (ce == cudaSuccess && coop && nb >= 1 &&
+    if (ce == cudaSuccess && coop && nb >= 1 && h->psync) {
+      h->panel_grid = h->sm_count;   // the look-ahead loop already made the slots and sync words
+    } else if (ce == cudaSuccess && coop && nb >= 1 &&
         cudaMalloc(&h->ppartials, (size_t)h->sm_count * 128) == cudaSuccess &&
         cudaMalloc(&h->pmins, (size_t)h->sm_count * 128) == cudaSuccess &&
         cudaMemset(h->ppartials, 0, (size_t)h->sm_count * 128) == cudaSuccess &&
@@ -552,6 +589,360 @@ void launch_panel_step(lps_handle h) {
                                                        h->world, h->plog, h->log_cap, h->pos2var);
 }
 
+
+// ---- TMA pass (lps_sweep.cuh) and look-ahead loop (lps_step.cuh) ------------------------------
+// cuTensorMapEncodeTiled comes from the driver through the runtime (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// row-major FP64 matrix [outer][pitch] seen as a 2-D tensor {inner, outer}; box {box_in, box_out}
+bool make_map(CUtensorMap* map, const double* base, unsigned long long inner, unsigned long long outer,
+              unsigned long long pitch, unsigned int box_in, unsigned int box_out) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstride[1] = {pitch * sizeof(double)};
+  const cuuint32_t box[2] = {box_in, box_out};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Shapes of the TMA pass the library is built with: <pending pivots held in registers, rows per thread per
+// stage, consumer warps> (SweepShape, lps_sweep.cuh).  pass_shape(): update_variant 10 / 11 / 12 pick one
+// explicitly (tuning), otherwise the default for the block size.
+using ShapeW12 = SweepShape<16, 4, 12>;   // 512 threads, 128 registers, three consumer warps per scheduler
+using ShapeW8 = SweepShape<16, 4, 8>;     // 384 threads, 168 registers, two consumer warps per scheduler
+using ShapeT8 = SweepShape<16, 8, 8>;     // ... with 8 rows per thread (16-row stages)
+using ShapeS8 = SweepShape<8, 4, 12>;     // small blocks (<= 8 pending pivots)
+
+int pass_shape(lps_handle h) {
+  if (h->block <= 8) return 3;
+  switch (h->opt.update_variant) {
+    case 11: return 1;
+    case 12: return 2;
+    default: return 0;
+  }
+}
+#define LPS_WITH_SHAPE(h_, ...)                    \
+  do {                                             \
+    switch (pass_shape(h_)) {                      \
+      case 1: { using Shape = ShapeW8; __VA_ARGS__; } break;  \
+      case 2: { using Shape = ShapeT8; __VA_ARGS__; } break;  \
+      case 3: { using Shape = ShapeS8; __VA_ARGS__; } break;  \
+      default: { using Shape = ShapeW12; __VA_ARGS__; } break; \
+    }                                              \
+  } while (0)
+
+int sweep_ks(lps_handle h) { return h->block <= 8 ? 8 : 16; }
+bool sweep_available(lps_handle h) {
+  return h->block > 1 && h->block <= 16 && h->comm && h->acols && encode_fn() != nullptr;
+}
+int pass_stage_rows(lps_handle h) { int r = 0; LPS_WITH_SHAPE(h, r = Shape::kSR); return r; }
+int pass_threads(lps_handle h) { int r = 0; LPS_WITH_SHAPE(h, r = Shape::kThreads); return r; }
+size_t pass_smem_bytes(lps_handle h) { size_t r = 0; LPS_WITH_SHAPE(h, r = Shape::kBytes); return r; }
+
+size_t step_smem_bytes(lps_handle h) {
+  return std::max(pass_smem_bytes(h), (size_t)kLookMax * pass_threads(h) * sizeof(double));
+}
+
+// tensor maps of the tableau buffer(s) and of the pending sets; `two` = second tableau buffer present
+int ensure_maps(lps_handle h, bool two) {
+  const int want = two ? 2 : 1;
+  if (h->tm_valid && h->tm_rows_set >= want) return LPS_OK;
+  const unsigned int bw = (unsigned int)std::min<long long>(kSwCols, h->ld);
+  const unsigned int bu = (unsigned int)std::min(sweep_ks(h), h->block);
+  const unsigned int sr = (unsigned int)pass_stage_rows(h);
+  bool ok = make_map(&h->tm_T[0], h->T, h->ld, h->m + 1, h->ld, bw, sr);
+  ok = ok && make_map(&h->tm_T[1], two ? h->T2 : h->T, h->ld, h->m + 1, h->ld, bw, sr);
+  for (int s2 = 0; s2 < 2 && ok; s2++) {
+    ok = make_map(&h->tm_A[s2], h->acols + (size_t)s2 * h->block * h->apitch, h->apitch, h->block, h->apitch, sr, bu) &&
+         make_map(&h->tm_R[s2], h->peers.rowbuf[h->rank] + (size_t)s2 * h->block * h->ld, h->ld, h->block, h->ld, bw, bu);
+  }
+  if (!ok) return fail(h, LPS_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  h->tm_valid = true;
+  h->tm_rows_set = want;
+  return LPS_OK;
+}
+
+template <typename K>
+int step_kernel_setup(lps_handle h, K kern, int threads, size_t smem) {
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int nb = 0;
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem);
+  if (ce != cudaSuccess || nb < 1) {
+    cudaGetLastError();
+    return fail(h, LPS_ERR_STATE, "the TMA pass kernel does not fit on an SM");
+  }
+  return LPS_OK;
+}
+
+int sweep_chunk_rows(lps_handle h, int ncta) {
+  int cr = h->opt.pass_chunk_rows;
+  if (cr <= 0) {
+    // about two dozen chunks per CTA, so the tail of the pass (CTAs finishing at different times) stays small
+    const long long bw = std::min<long long>(kSwCols, h->ld);
+    const long long nstrips = (h->ld + bw - 1) / bw;
+    cr = (int)(((long long)(h->m + 1) * nstrips) / (24ll * std::max(1, ncta)));
+    cr = std::min(cr, 240);
+  }
+  const int sr = pass_stage_rows(h);
+  cr = std::max(sr, (cr / sr) * sr);
+  return cr;
+}
+
+void fill_sweep_args(lps_handle h, SweepArgs& sw, int q, bool inplace, int cta0, int ncta) {
+  sw.ctl = h->ctls;
+  sw.Tbuf[0] = h->T;
+  sw.Tbuf[1] = inplace ? h->T : h->T2;
+  sw.ld = h->ld;
+  sw.rows = h->m + 1;
+  sw.chunk_rows = sweep_chunk_rows(h, ncta);
+  sw.bw = (int)std::min<long long>(kSwCols, h->ld);
+  sw.bu = std::min(sweep_ks(h), h->block);
+  sw.q = q;
+  sw.inplace = inplace ? 1 : 0;
+  sw.cta0 = cta0;
+  sw.ncta = ncta;
+}
+
+// the pass alone, in place, after kb_panel / kb_row (loop modes 5 and 6)
+int launch_sweep(lps_handle h) {
+  int rc = ensure_maps(h, false);
+  if (rc) return rc;
+  const size_t smem = pass_smem_bytes(h);
+  if (h->sweep_grid == 0) {
+    LPS_WITH_SHAPE(h, rc = step_kernel_setup(h, kb_sweep<Shape>, Shape::kThreads, smem));
+    if (rc) return rc;
+    h->sweep_grid = h->sm_count;
+  }
+  SweepArgs sw;
+  fill_sweep_args(h, sw, 0, true, 0, h->sweep_grid);
+  LPS_WITH_SHAPE(h, (kb_sweep<Shape><<<h->sweep_grid, Shape::kThreads, smem, h->stream>>>(sw, h->tm_T[0], h->tm_T[0],
+                                                                                        h->tm_A[0], h->tm_R[0])));
+  return LPS_OK;
+}
+
+bool use_look(lps_handle h) {
+  if (!sweep_available(h)) return false;
+  if (h->opt.loop_mode == 7) return true;
+  return h->opt.loop_mode == 0 && shard_bytes(h) > 64e6;
+}
+
+int look_panel_ctas(lps_handle h) {
+  int P = h->opt.panel_ctas;
+  if (P <= 0) {
+    // the panel is a latency chain with O((m + n) * pending) of L2 traffic per pivot: a handful of SMs hide it
+    // behind a multi-GB pass; a small shard's pass is short, so its panel gets more
+    const double bytes = shard_bytes(h);
+    P = bytes > 3e9 ? 8 : bytes > 1.2e9 ? 12 : 16;
+  }
+  return std::max(1, std::min(P, h->sm_count - 1));
+}
+
+// second tableau buffer, running vectors, sync words, tensor maps, kernel attributes
+int ensure_look(lps_handle h) {
+  const size_t need = (size_t)(h->m + 1) * (size_t)h->ld * sizeof(double);
+  if (need > h->T2_bytes) {
+    if (h->T2) cudaFree(h->T2);
+    h->T2 = nullptr;
+    h->T2_bytes = 0;
+    h->tm_valid = false;
+    cudaError_t ce = cudaMalloc(&h->T2, need);
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      return fail(h, LPS_ERR_NOMEM, "cudaMalloc(second tableau buffer of the look-ahead loop)", ce);
+    }
+    h->T2_bytes = need;
+  }
+  if ((size_t)h->m + 1 > h->bvec_cap) {
+    if (h->bvec) cudaFree(h->bvec);
+    CK(cudaMalloc(&h->bvec, ((size_t)h->m + 1 + 64) * sizeof(double)));
+    h->bvec_cap = (size_t)h->m + 1 + 64;
+  }
+  if ((size_t)h->ld > h->cvec_cap) {
+    if (h->cvec) cudaFree(h->cvec);
+    CK(cudaMalloc(&h->cvec, ((size_t)h->ld + 64) * sizeof(double)));
+    h->cvec_cap = (size_t)h->ld + 64;
+  }
+  if (!h->psync) {
+    CK(cudaMalloc(&h->ppartials, (size_t)h->sm_count * 128));
+    CK(cudaMalloc(&h->pmins, (size_t)h->sm_count * 128));
+    CK(cudaMalloc(&h->psync, 1024));
+    CK(cudaMemsetAsync(h->ppartials, 0, (size_t)h->sm_count * 128, h->stream));
+    CK(cudaMemsetAsync(h->pmins, 0, (size_t)h->sm_count * 128, h->stream));
+    CK(cudaMemsetAsync(h->psync, 0, 1024, h->stream));
+  }
+  int rc = ensure_maps(h, true);
+  if (rc) return rc;
+  if (h->step_grid == 0) {
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->dev));
+    if (!coop) return fail(h, LPS_ERR_STATE, "device does not support cooperative launch");
+    const size_t smem = step_smem_bytes(h);
+    if (h->sharded) LPS_WITH_SHAPE(h, rc = step_kernel_setup(h, kb_step<true, Shape>, Shape::kThreads, smem));
+    else LPS_WITH_SHAPE(h, rc = step_kernel_setup(h, kb_step<false, Shape>, Shape::kThreads, smem));
+    if (rc) return rc;
+    h->step_grid = h->sm_count;
+  }
+  return LPS_OK;
+}
+
+int launch_step(lps_handle h) {
+  StepArgs sa;
+  const int q = (int)(h->look_launches & 1u);
+  const int P = look_panel_ctas(h);
+  fill_sweep_args(h, sa.sw, q, false, P, h->step_grid - P);
+  sa.mloc = h->m;
+  sa.n = h->n;
+  sa.row0 = h->row0;
+  sa.row1 = h->row1;
+  sa.panel_ctas = P;
+  sa.block = h->block;
+  sa.Acols = h->acols;
+  sa.apitch = h->apitch;
+  sa.bvec = h->bvec;
+  sa.cvec = h->cvec;
+  sa.eps = h->opt.epsilon;
+  sa.inf = h->opt.inf;
+  sa.partials = h->ppartials;
+  sa.mins = h->pmins;
+  sa.syncw = h->psync;
+  sa.gwin = reinterpret_cast<PeerCand*>(h->psync + 192);
+  sa.ll_off = h->ll_off;
+  sa.peers = h->peers;
+  sa.rank = h->rank;
+  sa.world = h->world;
+  sa.plog = h->plog;
+  sa.log_cap = h->log_cap;
+  sa.pos2var = h->pos2var;
+  h->panel_launches += 1;
+  sa.tag0 = h->panel_launches * 64u;
+  h->look_launches += 1;
+  void* args[] = {&sa, &h->tm_T[0], &h->tm_T[1], &h->tm_A[q], &h->tm_R[q]};
+  const void* fn = nullptr;
+  if (h->sharded) LPS_WITH_SHAPE(h, fn = (const void*)kb_step<true, Shape>);
+  else LPS_WITH_SHAPE(h, fn = (const void*)kb_step<false, Shape>);
+  CK(cudaLaunchCooperativeKernel(fn, dim3(h->step_grid), dim3(pass_threads(h)), args, step_smem_bytes(h), h->stream));
+  return LPS_OK;
+}
+
+int run_look(lps_handle h, int64_t max_pivots, lps_run_result* res) {
+  const long long start_pivots = h->total_pivots;
+  const int S = h->block;
+  long long launches = 0;
+  if (h->panel_dirty && h->psync) {
+    CK(cudaMemsetAsync(h->psync, 0, 1024, h->stream));
+    h->panel_dirty = false;
+  }
+  CK(cudaEventRecord(h->ev_begin, h->stream));
+  // the tableau is fully applied between calls: the entering column and the running b column /
+  // objective row come straight from it
+  ks_begin_run<<<1, 1, 0, h->stream>>>(h->ctls, max_pivots, 1);
+  ks_first_positive<<<std::max(1, cdiv(h->n, 256)), 256, 0, h->stream>>>(h->ctls, h->T + (long long)h->m * h->ld, h->n,
+                                                                        h->opt.epsilon);
+  kb_init_vec<<<std::max(1, cdiv(std::max<long long>(h->m + 1, h->ld), 256)), 256, 0, h->stream>>>(
+      h->T, h->ld, h->m, h->n, h->bvec, h->cvec);
+  launches += 3;
+  h->look_launches = 0;
+  // blocks per host check: about 30 ms of device work
+  const double bytes = 16.0 * (double)(h->m + 1) * (double)(h->n + 1);
+  const double est_us = bytes / 5.0e6 + 16.0 * S;
+  long long batch = std::max(2ll, std::min((long long)(30000.0 / est_us), 256ll));
+  const bool timed = h->opt.time_kernels != 0;
+  if (timed) {
+    while ((long long)h->ev.size() < 2 * (batch + 1)) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->ev.push_back(e);
+    }
+  }
+  double upd_ms = 0.0;
+  long long upd_launches = 0, run_index = 0;     // run_index: launches of this run so far
+  long long remaining = (max_pivots < 0) ? -1 : (long long)max_pivots;
+  int rc = LPS_OK;
+  for (;;) {
+    // a capped run needs ceil(remaining / S) + 1 launches: the panel runs one block ahead of the pass
+    long long todo = batch;
+    if (remaining >= 0) todo = std::min(batch, (remaining + S - 1) / S + 1);
+    if (h->h_ctl->status != kRunning && run_index > 0) todo = 1;        // draining the last pending block
+    for (long long k = 0; k < todo; k++) {
+      if (timed) cudaEventRecord(h->ev[2 * k], h->stream);
+      rc = launch_step(h);
+      if (rc) return rc;
+      if (timed) cudaEventRecord(h->ev[2 * k + 1], h->stream);
+      launches++;
+    }
+    CK(cudaGetLastError());
+    rc = sync_ctl(h);
+    if (rc) return rc;
+    const long long done_now = h->h_ctl->npivots - h->total_pivots;
+    // passes happen in launches 1 .. sweeps_done of the run (launch 0 has nothing to apply yet)
+    const long long swept = (long long)h->h_ctls->sweeps_done;
+    for (long long k = 0; k < todo; k++) {
+      const long long r = run_index + k;
+      if (r >= 1 && r <= swept) {
+        if (timed) {
+          float ms = 0.f;
+          if (cudaEventElapsedTime(&ms, h->ev[2 * k], h->ev[2 * k + 1]) == cudaSuccess) upd_ms += ms;
+        }
+        upd_launches++;
+      }
+    }
+    run_index += todo;
+    h->total_pivots = h->h_ctl->npivots;
+    if (remaining >= 0) remaining -= done_now;
+    if (h->h_ctl->status != kRunning && (h->h_ctls->blk_pend[0] | h->h_ctls->blk_pend[1]) == 0) break;
+  }
+  // the tableau may have ended up in the second buffer: make it the handle's current one
+  if (h->h_ctls->cur_at[h->look_launches & 1u] == 1) {
+    std::swap(h->T, h->T2);
+    std::swap(h->T_bytes, h->T2_bytes);
+    std::swap(h->tm_T[0], h->tm_T[1]);
+  }
+  if (h->h_ctl->status == kCommTimeout) {
+    h->panel_dirty = true;
+    return fail(h, LPS_ERR_COMM, "shard: timed out waiting for a peer rank");
+  }
+  CK(cudaEventRecord(h->ev_end, h->stream));
+  CK(cudaEventSynchronize(h->ev_end));
+  h->next_valid = false;
+  h->col_holds = -1;
+  if (res) {
+    std::memset(res, 0, sizeof(*res));
+    res->verdict = h->h_ctl->status;
+    res->last_entering = h->h_ctl->e_cur;
+    res->last_leaving = h->h_ctl->l_cur;
+    res->npivots = h->total_pivots - start_pivots;
+    res->total_pivots = h->total_pivots;
+    double corner = 0.0;
+    CK(cudaMemcpy(&corner, h->T + (long long)h->m * h->ld + h->n, sizeof(double), cudaMemcpyDeviceToHost));
+    res->v = 0.0 - corner;
+    cudaEventElapsedTime(&res->device_ms, h->ev_begin, h->ev_end);
+    res->update_ms = (float)upd_ms;
+    res->update_launches = upd_launches;
+    res->kernel_launches = launches;
+  }
+  return LPS_OK;
+}
+
 int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   const long long start_pivots = h->total_pivots;
   const int S = h->block;
@@ -564,8 +955,8 @@ int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   CK(cudaEventRecord(h->ev_begin, h->stream));
   // the tableau is fully applied between calls, so the entering column comes from its objective row
   ks_begin_run<<<1, 1, 0, h->stream>>>(h->ctls, max_pivots, 1);
-  ks_first_positive<<<cdiv(h->n, 256), 256, 0, h->stream>>>(h->ctls, h->T + (long long)h->m * h->ld, h->n,
-                                                           h->opt.epsilon);
+  ks_first_positive<<<std::max(1, cdiv(h->n, 256)), 256, 0, h->stream>>>(h->ctls, h->T + (long long)h->m * h->ld, h->n,
+                                                                        h->opt.epsilon);
   launches += 2;
   // pivots per host check: about 30 ms of device work, whole blocks
   const double bytes = 16.0 * (double)(h->m + 1) * (double)(h->n + 1);
@@ -628,7 +1019,7 @@ int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
     h->panel_dirty = true;
     return fail(h, LPS_ERR_COMM, "shard: timed out waiting for a peer rank");
   }
-  if (h->h_ctls->blk_pending != 0) return fail(h, LPS_ERR_STATE, "blocked loop: pivots left pending after the last pass");
+  if ((h->h_ctls->blk_pend[0] | h->h_ctls->blk_pend[1]) != 0) return fail(h, LPS_ERR_STATE, "blocked loop: pivots left pending after the last pass");
   CK(cudaEventRecord(h->ev_end, h->stream));
   CK(cudaEventSynchronize(h->ev_end));
 #ifdef LPS_PANEL_TIMING
@@ -750,6 +1141,9 @@ int lps_destroy(lps_handle h) {
   if (h->partials) cudaFree(h->partials);
   if (h->d_ops) cudaFree(h->d_ops);
   if (h->acols) cudaFree(h->acols);
+  if (h->T2) cudaFree(h->T2);
+  if (h->bvec) cudaFree(h->bvec);
+  if (h->cvec) cudaFree(h->cvec);
   if (h->ppartials) cudaFree(h->ppartials);
   if (h->pmins) cudaFree(h->pmins);
   if (h->psync) cudaFree(h->psync);
@@ -900,6 +1294,12 @@ int lps_run(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   if (!h) return LPS_ERR_INVALID;
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
   CK(cudaSetDevice(h->dev));
+  if (use_look(h)) {
+    const int rc_look = ensure_look(h);
+    if (rc_look == LPS_OK) return run_look(h, max_pivots, res);
+    if (h->opt.loop_mode == 7 || rc_look != LPS_ERR_NOMEM) return rc_look;
+    // no room for the second tableau buffer: the serial blocked loop runs in place
+  }
   if (use_blocked(h)) return run_blocked(h, max_pivots, res);
   const long long start_pivots = h->total_pivots;
   long long launches = 0;
@@ -1186,7 +1586,9 @@ int lps_drop_column(lps_handle h, int j) {
   CK(cudaMemcpyAsync(p.data(), h->pos2var, p.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   p.erase(p.begin() + j);
-  CK(cudaMemcpy(h->pos2var, p.data(), p.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // on the handle's own (non-blocking) stream and waited for: later kernels on it swap entries of the map
+  CK(cudaMemcpyAsync(h->pos2var, p.data(), p.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   h->n -= 1;
   h->next_valid = false;
   h->col_holds = -1;

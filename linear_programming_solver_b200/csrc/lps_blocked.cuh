@@ -114,15 +114,15 @@ kb_col(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
   if (ctl->base.status != kRunning) return;
   const long long np = ctl->base.npivots;
   const unsigned int seq = (unsigned int)(np + 1);
-  const int t = ctl->blk_pending;
+  const int t = ctl->blk_pend[0];
   const int e = ctl->e_nx[seq & 1];
   __shared__ double s_re[kMaxBlock], s_rn[kMaxBlock], s_p[kMaxBlock];
   __shared__ int s_l[kMaxBlock], s_e[kMaxBlock];
   if ((int)threadIdx.x < t) {
     const int u = threadIdx.x;
-    s_l[u] = ctl->blk_l[u];
-    s_e[u] = ctl->blk_e[u];
-    s_p[u] = ctl->blk_p[u];
+    s_l[u] = ctl->blk_l2[0][u];
+    s_e[u] = ctl->blk_e2[0][u];
+    s_p[u] = ctl->blk_p2[0][u];
     s_rn[u] = Rrows[(long long)u * ld + n];
     s_re[u] = (e != kNone) ? Rrows[(long long)u * ld + e] : 0.0;
   }
@@ -201,7 +201,7 @@ kb_row(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
   const long long np = ctl->base.npivots;
   const unsigned int seq = (unsigned int)(np + 1);
   const int par = seq & 1;
-  const int t = ctl->blk_pending;
+  const int t = ctl->blk_pend[0];
   CommBlock* mine = peers.blk[rank];
   __shared__ int s_lw, s_verdict;
   __shared__ double s_pw;
@@ -246,9 +246,9 @@ kb_row(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
   const int lloc = l - row0;
   if (verdict == kRunning && (int)threadIdx.x < t) {
     const int u = threadIdx.x;
-    s_l[u] = ctl->blk_l[u];
-    s_e[u] = ctl->blk_e[u];
-    s_p[u] = ctl->blk_p[u];
+    s_l[u] = ctl->blk_l2[0][u];
+    s_e[u] = ctl->blk_e2[0][u];
+    s_p[u] = ctl->blk_p2[0][u];
     s_al[u] = i_own ? Acols[(long long)u * apitch + lloc] : 0.0;
     s_am[u] = Acols[(long long)u * apitch + mloc];
   }
@@ -320,10 +320,10 @@ kb_row(CtlS* ctl, const double* __restrict__ T, long long ld, int mloc, int n, i
   ctl->base.l_cur = l;
   ctl->base.p = p;
   ctl->owner = i_own ? rank : -1;
-  ctl->blk_e[t] = e;
-  ctl->blk_l[t] = i_own ? lloc : -1;
-  ctl->blk_p[t] = p;
-  ctl->blk_pending = t + 1;
+  ctl->blk_e2[0][t] = e;
+  ctl->blk_l2[0][t] = i_own ? lloc : -1;
+  ctl->blk_p2[0][t] = p;
+  ctl->blk_pend[0] = t + 1;
   plog[np % log_cap] = make_int2(e, l);
   int tmp = pos2var[e];                                   // exchangeIndexes, LPState.java:311-320
   pos2var[e] = pos2var[n + l];
@@ -509,12 +509,12 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
   const int mloc = a.mloc, n = a.n;
   long long np = ctl->base.npivots;
   const long long limit = ctl->base.pivot_limit;
-  int t = ctl->blk_pending;
+  int t = ctl->blk_pend[0];
   int e = ctl->e_nx[(np + 1) & 1];
   if (tid < t) {
-    s_l[tid] = ctl->blk_l[tid];
-    s_e[tid] = ctl->blk_e[tid];
-    s_p[tid] = ctl->blk_p[tid];
+    s_l[tid] = ctl->blk_l2[0][tid];
+    s_e[tid] = ctl->blk_e2[0][tid];
+    s_p[tid] = ctl->blk_p2[0][tid];
   }
   // my share of the rows in phase A (objective row included) and of the columns in phase B:
   // contiguous ranges, normally one row / one column per thread
@@ -839,10 +839,10 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
       ctl->base.l_cur = l;
       ctl->base.p = p;
       ctl->owner = i_own ? a.rank : -1;
-      ctl->blk_e[t] = e;
-      ctl->blk_l[t] = lloc;
-      ctl->blk_p[t] = p;
-      ctl->blk_pending = t + 1;
+      ctl->blk_e2[0][t] = e;
+      ctl->blk_l2[0][t] = lloc;
+      ctl->blk_p2[0][t] = p;
+      ctl->blk_pend[0] = t + 1;
       ctl->e_nx[par ^ 1] = e2;
       a.plog[np % a.log_cap] = make_int2(e, l);
       int tmp = a.pos2var[e];                              // exchangeIndexes, LPState.java:311-320
@@ -883,7 +883,7 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
   constexpr int kThreads = kFlushThreads * kLanes;
   constexpr int kCH = kU * kLanes * kG;            // rows per chunk
   static_assert(kU % 2 == 0, "16-byte copies of the pending columns");
-  const int t = ctl->blk_pending;
+  const int t = ctl->blk_pend[0];
   if (t == 0) return;
   extern __shared__ __align__(32) double smem[];
   double* const s_r = smem;                                      // [2][t][kStripCols]
@@ -894,9 +894,9 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid / kFlushThreads, ltid = tid % kFlushThreads;
   if (tid < t) {
-    s_l[tid] = ctl->blk_l[tid];
-    s_e[tid] = ctl->blk_e[tid];
-    s_p[tid] = ctl->blk_p[tid];
+    s_l[tid] = ctl->blk_l2[0][tid];
+    s_e[tid] = ctl->blk_e2[0][tid];
+    s_p[tid] = ctl->blk_p2[0][tid];
   }
   const int nstrips = (int)((ld + kStripCols - 1) / kStripCols);
   const int nrb = (mloc + 1 + kCH - 1) / kCH;                    // chunks per strip
@@ -1101,7 +1101,7 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
   if (s_last && tid == 0) {
     ctl->blk_ticket = 0;
     ctl->blk_queue = 0;
-    ctl->blk_pending = 0;
+    ctl->blk_pend[0] = 0;
   }
 }
 

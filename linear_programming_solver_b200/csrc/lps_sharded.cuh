@@ -117,14 +117,21 @@ struct CtlS {
   unsigned long long bar;     // persistent loop: grid-barrier counter
   unsigned long long upd_ns;  // persistent loop: accumulated phase-C time
   // blocked loop (lps_blocked.cuh): pivots committed but not yet applied to the tableau
-  int blk_pending;            // 0..kMaxBlock
+  int blk_pend[2];            // pending pivots of set 0 / 1, 0..kMaxBlock (the look-ahead loop alternates the sets;
+                              // the other blocked loops use set 0 only)
   unsigned int blk_ticket;    // last-CTA-done counter of kb_flush
   unsigned long long blk_queue;   // kb_flush: next unclaimed chunk
   unsigned long long bar_base;    // kb_panel: value of `bar` when the next cooperative launch starts
   unsigned long long dbg_ns[16];   // kb_panel phase clock of CTA 0 (LPS_PANEL_TIMING builds only)
-  int blk_e[kMaxBlock];       // entering column of pending pivot u
-  int blk_l[kMaxBlock];       // its leaving row as a LOCAL row index, -1 if another rank owns the row
-  double blk_p[kMaxBlock];    // its pivot element
+  int blk_e2[2][kMaxBlock];   // [set][u] entering column of pending pivot u
+  int blk_l2[2][kMaxBlock];   // its leaving row as a LOCAL row index, -1 if another rank owns the row
+  double blk_p2[2][kMaxBlock];   // its pivot element
+  // look-ahead loop (lps_step.cuh): the tableau ping-pongs between two buffers
+  int cur_at[2];              // [launch parity] which buffer holds the tableau when that launch starts
+  unsigned int sweeps_done;   // passes that applied at least one pivot (host bookkeeping of the timed launches)
+  int pad2_;
+  int blk_fill[2];            // pivots the panel put into set 0 / 1 (blk_pend is cleared by the pass that applies the
+                              // set — possibly while the panel of the same launch is still starting; blk_fill is not)
 };
 
 __global__ void ks_begin_run(CtlS* ctl, long long max_pivots, int reset_next) {
@@ -136,6 +143,9 @@ __global__ void ks_begin_run(CtlS* ctl, long long max_pivots, int reset_next) {
   ctl->bar = 0;
   ctl->bar_base = 0;
   ctl->upd_ns = 0;
+  ctl->cur_at[0] = ctl->cur_at[1] = 0;   // the tableau is in the handle's current buffer when a run starts
+  ctl->sweeps_done = 0;
+  ctl->blk_fill[0] = ctl->blk_fill[1] = 0;
   if (reset_next) ctl->e_nx[(ctl->base.npivots + 1) & 1] = kNone;
 }
 

@@ -35,7 +35,7 @@ class LPState:
                  coefficients: Optional[Dict[str, int]] = None,
                  epsilon: float = DEF_EPSILON, inf: float = DEF_INF, device: int = -1,
                  time_kernels: bool = False, loop_mode: int = 0, block_pivots: int = 0, _handle=None,
-                 _aux=False):
+                 _aux=False, update_variant: int = -1, panel_ctas: int = 0, pass_chunk_rows: int = 0):
         self._lib = N.load()
         self._h = c_void_p()
         self._names0 = None
@@ -48,6 +48,8 @@ class LPState:
         opts.epsilon, opts.inf, opts.device, opts.time_kernels = epsilon, inf, device, int(time_kernels)
         opts.loop_mode = int(loop_mode)
         opts.block_pivots = int(block_pivots)
+        opts.update_variant = int(update_variant)
+        opts.panel_ctas, opts.pass_chunk_rows = int(panel_ctas), int(pass_chunk_rows)   # tuning only
         rc = self._lib.lps_create(byref(self._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + self._lib.lps_status_string(rc).decode())
@@ -85,6 +87,8 @@ class LPState:
         opts.update_variant = int(kw.get("update_variant", -1))
         opts.loop_mode = int(kw.get("loop_mode", 0))
         opts.block_pivots = int(kw.get("block_pivots", 0))
+        opts.panel_ctas = int(kw.get("panel_ctas", 0))
+        opts.pass_chunk_rows = int(kw.get("pass_chunk_rows", 0))
         rc = st._lib.lps_create(byref(st._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + st._lib.lps_status_string(rc).decode())

@@ -52,7 +52,8 @@ class ShardedLPState(LPState):
                  v: float = 0.0, synthetic_seed: Optional[int] = None, pos_permille: int = 1000,
                  epsilon: float = LPState.DEF_EPSILON, inf: float = LPState.DEF_INF, device: int = -1,
                  time_kernels: bool = False, loop_mode: int = 0, block_pivots: int = 0,
-                 synthetic_kind: int = N.LPS_GEN_DENSE):
+                 synthetic_kind: int = N.LPS_GEN_DENSE, update_variant: int = -1, panel_ctas: int = 0,
+                 pass_chunk_rows: int = 0):
         self._lib = N.load()
         self._h = c_void_p()
         self._names0 = None
@@ -62,6 +63,8 @@ class ShardedLPState(LPState):
         opts.epsilon, opts.inf, opts.device, opts.time_kernels = epsilon, inf, device, int(time_kernels)
         opts.loop_mode = int(loop_mode)
         opts.block_pivots = int(block_pivots)
+        opts.update_variant = int(update_variant)
+        opts.panel_ctas, opts.pass_chunk_rows = int(panel_ctas), int(pass_chunk_rows)
         rc = self._lib.lps_create(byref(self._h), byref(opts))
         if rc != N.LPS_OK:
             raise LpsError(rc, "lps_create: " + self._lib.lps_status_string(rc).decode())

@@ -1,6 +1,8 @@
 """The blocked loop (lps_blocked.cuh): up to `block_pivots` pivots are deferred and applied in ONE
-pass over the tableau.  loop_mode=mode runs the panel as two launches per pivot (kb_col, kb_row),
-loop_mode=6 as one cooperative launch per block (kb_panel).  Every value must still be
+pass over the tableau.  loop_mode=5 runs the panel as two launches per pivot (kb_col, kb_row),
+loop_mode=6 as one cooperative launch per block (kb_panel) followed by the pass, loop_mode=7 is the
+look-ahead loop: one cooperative launch per block runs the TMA pass of block k (out of place) and the
+panel of block k+1 side by side (kb_step).  Every value must still be
 bit-identical to the pivot-per-pass kernels and to the binary64 oracle — pivot sequence, verdict,
 every cell.  `-m gpu`."""
 import threading
@@ -13,7 +15,7 @@ from oracle import tier_f
 pytestmark = pytest.mark.gpu
 
 VERDICT = {tier_f.OPTIMAL: 1, tier_f.UNBOUNDED: 2, tier_f.PIVOT_CAP: 3}
-MODES = [5, 6]
+MODES = [5, 6, 7]
 
 
 def _L():
@@ -49,9 +51,10 @@ def test_blocked_bit_exact_vs_tier_f(m, n, seed, block, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12])
 def test_blocked_flush_variants(variant, mode):
-    """every tile shape of the pass kernel gives the same bits (wide and tall cases, capped)"""
+    """every tile shape of the pass kernel gives the same bits (wide and tall cases, capped); 0-7 are the
+    cp.async kernel kb_flush (loop modes 5 and 6), 10-12 the shapes of the TMA pass"""
     L = _L()
     from linear_programming_solver_b200.lp_state import LPState
     for (m, n, seed, cap) in [(700, 5001, 2, 90), (2100, 530, 3, 70)]:
@@ -255,3 +258,62 @@ def test_blocked_multi_gpu(world, mode):
         assert np.array_equal(s.A, ref.A[s.row0:s.row1])
         assert np.array_equal(s.b, ref.b[s.row0:s.row1])
         assert np.array_equal(s.c, ref.c) and s.v == ref.v[0]
+
+
+@pytest.mark.parametrize("mode", [6, 7])
+@pytest.mark.parametrize("ctas,chunk", [(1, 12), (3, 24), (40, 0), (147, 48)])
+def test_look_ahead_role_split_and_chunking(mode, ctas, chunk):
+    """the result may not depend on how many CTAs run the panel, nor on the chunk height of the pass"""
+    from linear_programming_solver_b200.lp_state import LPState
+    m, n, seed, cap = 900, 2100, 4, 150
+    A, b, c = tier_f.gen_dense_feasible(m, n, seed)
+    ref = tier_f.TierFState(A.copy(), b.copy(), c.copy(), nthreads=4)
+    status, k = ref.run(cap)
+    st = LPState.synthetic_dense(m, n, seed, 1000, loop_mode=mode, panel_ctas=ctas, pass_chunk_rows=chunk)
+    res = st.run(cap)
+    assert res.verdict == VERDICT[status] and res.npivots == k
+    _same_state(st, ref)
+
+
+@pytest.mark.parametrize("mode", [6, 7])
+def test_look_ahead_repeated_runs_and_buffer_swaps(mode):
+    """many short runs: the tableau ends up in either buffer of the out-of-place pass, partial blocks,
+    caps at every position of a block"""
+    L = _L()
+    m, n = 120, 200
+    A, b, c = tier_f.gen_dense_feasible(m, n, 9)
+    ref = tier_f.TierFState(A.copy(), b.copy(), c.copy())
+    ref.run()
+    st = L.LPState(A, b, c, m, n, loop_mode=mode, block_pivots=4)
+    done = 0
+    for step in [1, 2, 3, 4, 5, 7, 8, 9, 1, 16, 17]:
+        r = st.run(step)
+        done += r.npivots
+        assert st.pivot_log == ref.log[:done]
+        if r.verdict != 3:
+            break
+        again = tier_f.TierFState(A.copy(), b.copy(), c.copy())
+        again.run(done)
+        assert np.array_equal(st.A, again.A) and np.array_equal(st.b, again.b) and np.array_equal(st.c, again.c)
+    r = st.run()
+    assert r.verdict == 1 and r.total_pivots == len(ref.log)
+    _same_state(st, ref)
+
+
+@pytest.mark.parametrize("mode", [6, 7])
+def test_handle_reloaded_with_a_larger_lp(mode):
+    """one handle, a small LP and then a large one: the pass kernel chosen for the second size must get
+    its shared-memory opt-in too"""
+    L = _L()
+    from linear_programming_solver_b200.lp_state import _dp
+    A, b, c = tier_f.gen_dense_feasible(40, 60, 1)
+    st = L.LPState(A, b, c, 40, 60, loop_mode=mode, update_variant=0 if mode == 6 else -1)
+    st.run(20)
+    m, n = 2600, 2100
+    A, b, c = tier_f.gen_dense_feasible(m, n, 2)
+    ref = tier_f.TierFState(A.copy(), b.copy(), c.copy(), nthreads=4)
+    ref.run(40)
+    st._ck(st._lib.lps_load(st._h, m, n, _dp(A), n, _dp(b), _dp(c), 0.0), "lps_load")
+    r = st.run(40)
+    assert r.npivots == 40
+    _same_state(st, ref)

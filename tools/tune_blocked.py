@@ -17,17 +17,22 @@ def main():
     ap.add_argument("passes", type=int, nargs="?", default=6)
     ap.add_argument("--blocks", default="4,8,16,24,32")
     ap.add_argument("--variants", default="0")
-    ap.add_argument("--mode", type=int, default=6, help="5 = two launches per pivot, 6 = one cooperative launch per block")
+    ap.add_argument("--mode", type=int, default=6, help="5 = two launches per pivot, 6 = one cooperative panel launch "
+                    "per block + the pass, 7 = look-ahead loop (panel and pass side by side)")
+    ap.add_argument("--panel", default="0", help="look-ahead loop: CTAs of the panel role (comma list, 0 = auto)")
+    ap.add_argument("--chunk", default="0", help="TMA pass: rows per chunk (comma list, 0 = auto)")
     a = ap.parse_args()
-    for S in [int(x) for x in a.blocks.split(",")]:
-        for var in [int(x) for x in a.variants.split(",")]:
+    combos = [(S, var, P, ch) for S in [int(x) for x in a.blocks.split(",")] for var in [int(x) for x in a.variants.split(",")]
+              for P in [int(x) for x in a.panel.split(",")] for ch in [int(x) for x in a.chunk.split(",")]]
+    for S, var, P, ch in combos:
+        if True:
             st = L.LPState.synthetic_dense(a.m, a.n, 0, 1000, time_kernels=True, loop_mode=a.mode, block_pivots=S,
-                                           update_variant=var)
+                                           update_variant=var, panel_ctas=P, pass_chunk_rows=ch)
             st.run(2 * S)  # warm-up
             r = st.run(a.passes * S)
             bytes_pp = st.algorithmic_bytes_per_pivot()
             pass_ms = r.update_ms / max(r.update_launches, 1)
-            rec = dict(block=S, variant=var, mode=a.mode, m=a.m, n=a.n, pivots=int(r.npivots),
+            rec = dict(block=S, variant=var, mode=a.mode, panel_ctas=P, chunk_rows=ch, m=a.m, n=a.n, pivots=int(r.npivots),
                        pivots_per_s=1e3 * r.npivots / r.device_ms, us_per_pivot=1e3 * r.device_ms / max(r.npivots, 1),
                        pass_ms=pass_ms, pass_dram_gbs=bytes_pp / pass_ms / 1e6 if pass_ms else None,
                        panel_us_per_pivot=1e3 * (r.device_ms - r.update_ms) / max(r.npivots, 1),
