@@ -7,7 +7,8 @@ Workload (BASELINE.json configs[3], the configuration the metric is quoted on): 
 dense LP, 20,000 constraints x 40,000 variables, max with <= rows (SURVEY.md §8d generator,
 seed 0), FP64 tableau of 6.4 GB resident in HBM.  One *step* = `--pivots-per-step` pivots of
 the running solve (getEntering / getLeaving / pivot on the device, LPSolver.java:101-112); the
-default loop is the blocked one (16 pivots share one pass over the tableau, lps_blocked.cuh).
+default loop is the look-ahead blocked one: 16 pivots share one pass over the tableau, and the
+panel that decides the NEXT 16 runs beside the pass (lps_step.cuh).
 
 The JSON line carries, beside the contract keys:
   value      pivots/s, whole job, inputs already in HBM, CUDA-event time on the library's
@@ -15,14 +16,26 @@ The JSON line carries, beside the contract keys:
   e2e        the same metric through the reference-facing call path with HOST buffers:
              lps_load (H2D of the whole tableau from pinned memory) + run + read-back of
              b, c, v and the position map, wall clock around synchronous calls
-  roofline   tableau-update kernel: algorithmic bytes 16(m+1)(n+1) per launch / its mean
-             CUDA-event duration over the timed region, against MEASURED_PEAKS.json hbm_gbs
+  roofline   the pass kernel (one launch = one read + one write of the local tableau, all pending
+             pivots applied): `achieved` = bytes it moves / mean CUDA-event launch time, `frac` = that
+             over MEASURED_PEAKS.json hbm_gbs (a physical fraction); `pivot_equiv_*` credit SURVEY 8d's
+             16(m+1)(n+1) bytes per pivot instead; `fp64` holds the second roof (issue rate of the
+             separately rounded DMUL + DADD mix, probed live with lps_measure_fp64_issue_rate)
+  parity     SHA-256 of the whole (entering, leaving) log and of the gathered b column after the
+             warm-up + timed pivots, compared with tests/golden/bench_c4_seed0_digests.json (made by
+             the pivot-per-pass kernels on one GPU, prefix-checked against the CPU twin); a
+             mismatch makes the run exit non-zero: neither the loop shape nor the row partition
+             may change results (LPState.java:222-223)
   cpu_baseline  the oracle's C binary64 twin of LPState.pivotConcurrently (kind "port";
              the Java reference cannot run: no JVM) on the box's host cores, bounded sample
+  secondary  N = 1 only: the pivot-per-pass kernel's own roofline line (50 pivots), BASELINE
+             configs[1] (1,000 x 1,000 solved to optimality) and configs[2] (10,000 x 10,000 with
+             mixed rows: phase 1 on the device, capped), and an end-to-end full solve
 
 `--impl reference` times that CPU port alone on the same config (all host threads).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,9 +48,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "pivots_per_sec"
 UNIT = "pivots/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the 20000x40000
-# workload, from the committed ncu --set full captures (profiles/): key = (config, pivots per launch)
-NCU_TRAFFIC = {("n1", 1): 12.756e9, ("n1", 16): 13.040e9}
+DIGESTS = os.path.join(ROOT, "tests", "golden", "bench_c4_seed0_digests.json")
+TRAFFIC = os.path.join(ROOT, "profiles", "r02_traffic.json")
 
 
 def parse_args():
@@ -54,16 +66,32 @@ def parse_args():
     ap.add_argument("--cpu-pivots", type=int, default=0, help="0 = sized for ~10-30 s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--loop-mode", type=int, default=0,
-                    help="0 auto (blocked loop at this size), 1 three kernels per pivot, 2 persistent loop, 5 blocked loop")
+                    help="0 auto (look-ahead blocked loop at this size), 1 three kernels per pivot, 2 persistent loop, "
+                         "5/6 serial blocked loops, 7 look-ahead blocked loop")
     ap.add_argument("--block", type=int, default=0, help="pivots per tableau pass of the blocked loop (0 = library default, 1 = off)")
+    ap.add_argument("--panel-ctas", type=int, default=0, help="look-ahead loop: SMs given to the panel (0 = auto)")
     return ap.parse_args()
 
 
 def workload_name(m, n):
     return "synthetic dense LP %dx%d (max, <= rows, seed-generated, FP64 tableau %.2f GB)" % (
         m, n, 8.0 * (m + 1) * (n + 1) / 1e9)
+
+
+def config_block(m, n, seed):
+    """identical in both arms (the driver compares them): everything run-specific lives in `details`"""
+    return {"workload": workload_name(m, n), "seed": seed}
+
+
+def host_threads():
+    """cores this process may use — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def measured_peak():
@@ -74,30 +102,53 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def roofline_block(bytes_pp, pivots, upd_ms, upd_n, kernel_names, peak, peak_src, traffic=None):
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+    ncu --set full capture for this shard size (profiles/r02_traffic.json), or None"""
+    try:
+        with open(TRAFFIC) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+def roofline_block(bytes_pp, pivots, upd_ms, upd_n, kernel_names, peak, peak_src, traffic=None, fp64_peak=None,
+                   cells=None):
     """The dominant kernel's roofline entry.
 
     One launch of the pass kernel applies `pivots/upd_n` pivots (1 for the pivot-per-pass kernels,
-    block_pivots for the blocked loop).  `achieved` is the contract's figure: ALGORITHMIC bytes per
-    launch = 16(m+1)(n+1) per pivot x pivots per launch, over the mean launch time — it exceeds the
-    HBM peak when several pivots share one pass, which is the point of the blocked loop.  The kernel's
-    real DRAM rate (one read + one write of the tableau per launch) is `dram_achieved` / `dram_frac`."""
+    block_pivots for the blocked loops) and moves the local tableau once: one 8-byte read and one 8-byte
+    write per cell = 16(m+1)(n+1) bytes = `bytes_pp`.  `achieved` / `frac` are what the kernel physically
+    sustains against the measured HBM peak.  SURVEY 8d's per-pivot credit (the same bytes for EVERY pivot
+    the launch applies) is reported as `pivot_equiv_*`: it exceeds the peak when pivots share a pass, which
+    is the point of the blocked loop.  With S pivots per pass the kernel also issues 2 S FP64 instructions per
+    cell (separately rounded multiply and subtract): `fp64` holds that roof."""
     upd_n = max(int(upd_n), 1)
     avg_ms = upd_ms / upd_n
     per_launch = pivots / upd_n
-    achieved = bytes_pp * per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
     dram = bytes_pp / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+    equiv = dram * per_launch
     blocked = per_launch > 1.5
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "kernel": kernel_names[1 if blocked else 0], "launches": upd_n, "avg_ms": avg_ms,
-            "peak_source": peak_src, "pivots_per_launch": per_launch,
-            "bytes_per_launch": int(bytes_pp * per_launch), "dram_bytes_per_launch": int(bytes_pp),
-            "dram_achieved": dram, "dram_frac": dram / peak, "dram_frac_of_8tbs": dram / 8000.0,
-            "frac_of_8tbs": achieved / 8000.0,
-            "note": ("blocked loop: %.1f pivots are replayed per pass, so the pass moves 16(m+1)(n+1) bytes once for "
-                     "all of them; `achieved` counts the per-pivot algorithmic bytes (SURVEY 8d), `dram_achieved` the "
-                     "bytes the kernel really moves; at this block size the pass is FP64-issue-bound, not HBM-bound"
-                     % per_launch) if blocked else "one pivot per pass"}
+    rl = {"bound": "hbm", "achieved": dram, "peak": peak, "unit": "GB/s", "frac": dram / peak,
+          "traffic": traffic, "kernel": kernel_names[1 if blocked else 0], "launches": upd_n, "avg_ms": avg_ms,
+          "peak_source": peak_src, "pivots_per_launch": per_launch, "bytes_per_launch": int(bytes_pp),
+          "frac_of_8tbs": dram / 8000.0,
+          "pivot_equiv_achieved": equiv, "pivot_equiv_frac": equiv / peak, "pivot_equiv_frac_of_8tbs": equiv / 8000.0,
+          "note": ("%.1f pivots are replayed per pass: the pass moves 16(m+1)(n+1) bytes once for all of them. "
+                   "`achieved`/`frac` are the bytes the kernel really moves per second; `pivot_equiv_*` credit those "
+                   "bytes once per pivot (SURVEY 8d)" % per_launch) if blocked else "one pivot per pass"}
+    if cells and avg_ms:
+        inst = 2.0 * per_launch * cells / (avg_ms * 1e-3)       # DMUL + DADD per cell per pivot
+        rl["fp64"] = {"achieved_tinst_s": inst / 1e12, "peak": (fp64_peak / 1e12) if fp64_peak else None,
+                      "frac": (inst / fp64_peak) if fp64_peak else None, "unit": "T thread-inst/s",
+                      "peak_source": "lps_measure_fp64_issue_rate: DMUL + DADD chains, 256 threads x 4 CTAs per SM, "
+                                     "probed right after the timed region (same power state)"}
+        if fp64_peak:
+            t_hbm, t_f = bytes_pp / (peak * 1e9), 2.0 * per_launch * cells / fp64_peak
+            rl["binding_roof"] = "hbm" if t_hbm >= t_f else "fp64"
+            rl["roof_ms"] = {"hbm": 1e3 * t_hbm, "fp64": 1e3 * t_f}
+            rl["frac_of_binding_roof"] = max(t_hbm, t_f) / (avg_ms * 1e-3)
+    return rl
 
 
 class ClockSampler:
@@ -165,6 +216,42 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def digest_log(pairs):
+    import numpy as np
+    return hashlib.sha256(np.asarray(pairs, dtype=np.int32).reshape(-1, 2).tobytes()).hexdigest()
+
+
+def digest_b(b):
+    import numpy as np
+    return hashlib.sha256(np.ascontiguousarray(b, dtype=np.float64).tobytes()).hexdigest()
+
+
+def parity_block(m, n, seed, total_pivots, log, b_global, usable=True, why=""):
+    """digests of this run against the committed single-GPU table; ok is True / False / None (nothing to compare)"""
+    rec = {"pivots": int(total_pivots), "log_sha256": digest_log(log), "b_sha256": digest_b(b_global),
+           "ok": None, "against": os.path.relpath(DIGESTS, ROOT)}
+    if not usable:
+        rec["note"] = why
+        return rec
+    try:
+        with open(DIGESTS) as f:
+            tab = json.load(f)
+    except Exception as ex:  # noqa: BLE001
+        rec["note"] = "no committed digest table: %s" % ex
+        return rec
+    if (tab.get("m"), tab.get("n"), tab.get("seed")) != (m, n, seed):
+        rec["note"] = "the committed table is for %sx%s seed %s" % (tab.get("m"), tab.get("n"), tab.get("seed"))
+        return rec
+    want = tab["digests"].get(str(int(total_pivots)))
+    if want is None:
+        rec["note"] = "no committed digest after %d pivots (the table has multiples of 256 up to %s)" % (
+            total_pivots, max(int(k) for k in tab["digests"]))
+        return rec
+    rec["ok"] = bool(want["log_sha256"] == rec["log_sha256"] and want["b_sha256"] == rec["b_sha256"])
+    rec["made_by"] = tab.get("made_by")
+    return rec
+
+
 def cpu_port_rate(A, b, c, pivots, threads):
     """pivots/s of the oracle's C twin of pivotConcurrently on host cores (bench-only use of oracle/)."""
     from oracle import tier_f
@@ -172,7 +259,7 @@ def cpu_port_rate(A, b, c, pivots, threads):
     t0 = time.perf_counter()
     status, k = st.run(pivots)
     dt = time.perf_counter() - t0
-    return (k / dt if dt > 0 else 0.0), k, dt
+    return (k / dt if dt > 0 else 0.0), k, dt, st.log[:k]
 
 
 def run_reference(args):
@@ -181,7 +268,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import tier_f
-    threads = tier_f.lib().tf_max_threads()
+    threads = host_threads()
     m, n = args.m, args.n
     A, b, c = tier_f.gen_dense_feasible(m, n, args.seed, nthreads=threads)
     st = tier_f.TierFState(A, b, c, nthreads=threads)
@@ -205,16 +292,85 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": workload_name(m, n), "pivots_per_step": per_step},
+        "data": "synthetic", "config": config_block(m, n, args.seed),
+        "details": {"pivots_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "C binary64 port of LPState.pivotConcurrently (oracle/tier_f.c); the Java reference "
-                "cannot run (no JVM in the image); an upper bound on its BigDecimal speed",
+        "note": "C binary64 port of LPState.pivotConcurrently (oracle/tier_f.c) with every core this process may "
+                "use (sched_getaffinity, not OMP_NUM_THREADS); the Java reference cannot run (no JVM in the image); "
+                "an upper bound on its BigDecimal speed",
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
+def loop_name(rl, loop_mode):
+    if rl["pivots_per_launch"] <= 1.5:
+        return "one tableau pass per pivot"
+    kind = "look-ahead blocked loop (panel of block k+1 beside the pass of block k)" if loop_mode in (0, 7) \
+        else "serial blocked loop"
+    return "%s: %.1f pivots per tableau pass" % (kind, rl["pivots_per_launch"])
+
+
+def secondary_records(L, args, local_rank, peak, peak_src):
+    """N = 1 extras the driver would otherwise never see (VERDICT r1 #4d, #7): short, after the main numbers."""
+    import numpy as np
+    from oracle import tier_f
+    out = {}
+    m, n = args.m, args.n
+    # (1) the pivot-per-pass kernel at the same size: its own roofline line
+    try:
+        st = L.LPState.synthetic_dense(m, n, args.seed, 1000, device=local_rank, time_kernels=True, loop_mode=1,
+                                       block_pivots=1)
+        st.run(8)
+        r = st.run(50)
+        rl = roofline_block(st.algorithmic_bytes_per_pivot(), r.npivots, r.update_ms, r.update_launches,
+                            ("lps::k_update", "-"), peak, peak_src, traffic=ncu_traffic("k_update_n1"))
+        out["pivot_per_pass"] = {"pivots": int(r.npivots), "value": r.npivots / (r.device_ms / 1e3), "unit": UNIT,
+                                 "roofline": rl, "what": "loop_mode=1: k_ratio -> k_scale_row -> k_update, one pass per pivot"}
+        st.close()
+    except Exception as ex:  # noqa: BLE001
+        out["pivot_per_pass"] = {"error": str(ex)}
+    # (2) BASELINE configs[1]: 1,000 x 1,000, solved to optimality
+    try:
+        A, b, c = tier_f.gen_dense_feasible(1000, 1000, 0)
+        st = L.LPState(A, b, c, 1000, 1000, device=local_rank)
+        st.run(64)
+        st.close()
+        st = L.LPState(A, b, c, 1000, 1000, device=local_rank)
+        t0 = time.perf_counter()
+        r = st.run()
+        wall = time.perf_counter() - t0
+        out["c2_1000x1000"] = {"verdict": int(r.verdict), "pivots": int(r.npivots), "value": r.npivots / (r.device_ms / 1e3),
+                               "unit": UNIT, "device_ms": r.device_ms, "wall_s": wall, "objective": st.v,
+                               "log_sha256": digest_log(st.pivot_log),
+                               "what": "BASELINE configs[1], full solve, persistent pivot-per-pass loop (8 MB: L2-resident)"}
+        st.close()
+    except Exception as ex:  # noqa: BLE001
+        out["c2_1000x1000"] = {"error": str(ex)}
+    # (3) BASELINE configs[2]: 10,000 x 10,000 mixed rows, phase 1 on the device, capped
+    try:
+        mm = nn = 10000
+        A, b, c = tier_f.gen_mixed_rows(mm, nn, 0, True)
+        k = tier_f.min_in_b(b)
+        st = L.LPState.aux(A, b, mm, nn, device=local_rank, time_kernels=True)
+        st.pivot(nn, k)                                   # LPSolver.java:138
+        st.run(512)
+        r = st.run(8192)
+        bytes_pp = st.algorithmic_bytes_per_pivot()
+        rl = roofline_block(bytes_pp, r.npivots, r.update_ms, r.update_launches, ("lps::k_update", "lps::kb_step"),
+                            peak, peak_src, traffic=ncu_traffic("kb_step_c3"), cells=(mm + 1) * (nn + 2))
+        out["c3_10000x10000_phase1"] = {"verdict": int(r.verdict), "pivots": int(r.npivots),
+                                        "value": r.npivots / (r.device_ms / 1e3), "unit": UNIT, "roofline": rl,
+                                        "negative_rhs_rows": int((b < 0).sum()),
+                                        "what": "BASELINE configs[2]: aux LP 10,000 x 10,001 built in HBM, forced pivot, "
+                                                "512 warm-up + 8,192 timed phase-1 pivots (capped)"}
+        st.close()
+    except Exception as ex:  # noqa: BLE001
+        out["c3_10000x10000_phase1"] = {"error": str(ex)}
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -237,11 +393,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world > 1:
         from linear_programming_solver_b200 import sharded
-        return sharded.bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_name,
-                                     measured_peak, ClockSampler, roofline_block)
+        return sharded.bench_sharded(args, dist, rank, world, local_rank, sys.modules[__name__])
 
     m, n, P = args.m, args.n, args.pivots_per_step
-    kw = dict(device=local_rank, time_kernels=True, loop_mode=args.loop_mode, block_pivots=args.block)
+    kw = dict(device=local_rank, time_kernels=True, loop_mode=args.loop_mode, block_pivots=args.block,
+              panel_ctas=args.panel_ctas)
     if args.variant >= 0:
         kw["update_variant"] = args.variant
     st = L.LPState.synthetic_dense(m, n, args.seed, 1000, **kw)
@@ -255,13 +411,17 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.wait_first()
+    total = 0
+    restarts = 0
     for _ in range(args.warmup):
-        st.run(P)
+        r = st.run(P)
+        total += r.npivots
+        if r.verdict != 3:
+            restarts += 1
     barrier()
     sampler.mark()
     dev_ms, upd_ms, upd_n, launches, pivots = 0.0, 0.0, 0, 0, 0
     t0 = time.perf_counter()
-    restarts = 0
     for _ in range(args.steps):
         need = P
         while need > 0:
@@ -280,30 +440,39 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
+    total += pivots
     if pivots != args.steps * P:
         raise SystemExit("pivot count mismatch: %d != %d" % (pivots, args.steps * P))
+    fp64_peak = st.measure_fp64_issue_rate(100.0)          # right after the timed region: same power state
     value = pivots / (dev_ms / 1e3)
     peak, peak_src = measured_peak()
-    rl = roofline_block(bytes_pp, pivots, upd_ms, upd_n, ("lps::k_update", "lps::kb_flush"), peak, peak_src,
-                        traffic=NCU_TRAFFIC.get(("n1", round(pivots / max(upd_n, 1)))))
+    per_launch = round(pivots / max(upd_n, 1))
+    kernels = ("lps::k_update", "lps::kb_step (pass role: sweep_role)" if args.loop_mode in (0, 7) else "lps::kb_flush / kb_sweep")
+    rl = roofline_block(bytes_pp, pivots, upd_ms, upd_n, kernels, peak, peak_src,
+                        traffic=ncu_traffic("kb_step_n1" if per_launch > 1 else "k_update_n1"), fp64_peak=fp64_peak,
+                        cells=(m + 1) * (n + 1))
+    parity = parity_block(m, n, args.seed, total, st.pivot_log, st.b, usable=(restarts == 0),
+                          why="the LP was solved to a verdict and regenerated inside the run")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(m, n), "pivots_per_step": P, "seed": args.seed,
-                   "loop": "blocked: %.1f pivots per tableau pass" % rl["pivots_per_launch"]
-                           if rl["pivots_per_launch"] > 1.5 else "one tableau pass per pivot",
-                   "l2": "tableau (6.4 GB) is far larger than the 126 MB L2; no flush needed",
-                   "timing": "CUDA events on the library's stream around each step",
-                   "restarts": restarts},
+        "config": config_block(m, n, args.seed),
+        "details": {"pivots_per_step": P, "loop": loop_name(rl, args.loop_mode),
+                    "l2": "tableau (6.4 GB) is far larger than the 126 MB L2; no flush needed",
+                    "timing": "CUDA events on the library's stream around each step; the pass kernel's launches are "
+                              "bracketed by their own events on the same stream",
+                    "restarts": restarts},
         "gpu_launches": int(launches),
         "loop_gbs": bytes_pp * pivots / (dev_ms * 1e-3) / 1e9,
         "frac_of_8tbs": bytes_pp * pivots / (dev_ms * 1e-3) / 1e9 / 8000.0,
         "loop_dram_gbs": bytes_pp * upd_n / (dev_ms * 1e-3) / 1e9,
         "wall_s": wall,
         "roofline": rl,
+        "parity": parity,
         "clocks": clocks,
     }
+    gpu_log_head = st.pivot_log[:64]
     st.close()
 
     # ---- host copy of the same input (untimed): generated on the device, read back ----
@@ -324,7 +493,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             s = L.LPState(A_host, b_host, c_host, m, n, device=local_rank, loop_mode=args.loop_mode,
-                          block_pivots=args.block)                                # H2D of the tableau
+                          block_pivots=args.block, panel_ctas=args.panel_ctas)    # H2D of the tableau
             r = s.run(Pe)
             out_b, out_c, out_v, out_pos = s.b, s.c, s.v, s.positions         # D2H of the result
             dt = time.perf_counter() - t0
@@ -334,32 +503,67 @@ def run_ours(args):
                        "h2d_bytes_per_step": int(8 * (m * n + m + n)),
                        "d2h_bytes_per_step": int(8 * (m + n + 1) + 4 * (m + n)),
                        "pivots_per_call": Pe, "seconds_per_call": best,
-                       "what": "LPState(A,b,c) from pinned host memory + run(%d) + read b,c,v,positions" % Pe}
+                       "what": "LPState(A,b,c) from pinned host memory + run(%d) + read b,c,v,positions; the 6.4 GB "
+                               "copy is a fixed cost per solve, so the figure grows with the pivots per call "
+                               "(e2e_full_solve below: a whole solve)" % Pe}
+        if not args.no_secondary:
+            # a whole solve through the same path: same A and b, costs positive for 1 % of the columns so
+            # that the first-positive rule terminates; 16,236 pivots
+            try:
+                g = L.LPState.synthetic_dense(m, n, args.seed, 10, device=local_rank)
+                c_full = g.c
+                g.close()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                s = L.LPState(A_host, b_host, c_full, m, n, device=local_rank, loop_mode=args.loop_mode,
+                              block_pivots=args.block, panel_ctas=args.panel_ctas)
+                r = s.run()
+                out_b, out_c, out_v, out_pos = s.b, s.c, s.v, s.positions
+                dt = time.perf_counter() - t0
+                line["e2e_full_solve"] = {"value": r.npivots / dt, "unit": UNIT, "pivots": int(r.npivots),
+                                          "verdict": int(r.verdict), "seconds": dt, "objective": out_v,
+                                          "log_sha256": digest_log(s.pivot_log), "b_sha256": digest_b(out_b),
+                                          "cpu_twin_digests": "profiles/r01_parity_c4_cpu_twin.json",
+                                          "what": "host buffers -> optimal verdict -> results on the host, "
+                                                  "20,000 x 40,000 LP with 1 % positive costs"}
+                s.close()
+            except Exception as ex:  # noqa: BLE001
+                line["e2e_full_solve"] = {"error": str(ex)}
     # ---- CPU baseline on the same input (bounded sample) ----
     if not args.no_cpu_baseline:
-        from oracle import tier_f
-        threads = tier_f.lib().tf_max_threads()
+        threads = host_threads()
         A_cpu = np.array(A_host, copy=True)
-        rate1, k1, dt1 = cpu_port_rate(A_cpu, b_host.copy(), c_host.copy(), 2, threads)
+        rate1, k1, dt1, _ = cpu_port_rate(A_cpu, b_host.copy(), c_host.copy(), 2, threads)
         want = args.cpu_pivots or max(3, min(60, int(15.0 * rate1)))
         A_cpu[...] = A_host
-        rate, k, dt = cpu_port_rate(A_cpu, b_host.copy(), c_host.copy(), want, threads)
+        rate, k, dt, cpu_log = cpu_port_rate(A_cpu, b_host.copy(), c_host.copy(), want, threads)
+        same = [tuple(x) for x in cpu_log] == [tuple(x) for x in gpu_log_head[:k]]
         line["cpu_baseline"] = {
             "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "first %d pivots of the same %dx%d LP in %.1f s, C binary64 twin of "
-                      "LPState.pivotConcurrently with %d threads (reference THREAD_AMOUNT is 4)" % (k, m, n, dt, threads)}
+                      "LPState.pivotConcurrently with %d threads (reference THREAD_AMOUNT is 4)" % (k, m, n, dt, threads),
+            "same_pivots_as_gpu": bool(same)}
+        line["parity"]["cpu_prefix_pivots"] = int(k)
+        line["parity"]["cpu_prefix_ok"] = bool(same)
         # SURVEY 8d also asks for the reference's own thread count (THREAD_AMOUNT = 4, LPState.java:22);
         # a short extra sample, never allowed to cost the line
         try:
             if threads > 4:
                 A_cpu[...] = A_host
-                rate4, k4, dt4 = cpu_port_rate(A_cpu, b_host.copy(), c_host.copy(), max(2, min(12, int(4.0 * rate))), 4)
+                rate4, k4, dt4, _ = cpu_port_rate(A_cpu, b_host.copy(), c_host.copy(), max(2, min(12, int(4.0 * rate))), 4)
                 line["cpu_baseline"]["value_4_threads"] = rate4
                 line["cpu_baseline"]["sample_4_threads"] = "first %d pivots in %.1f s with 4 threads" % (k4, dt4)
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"]["value_4_threads"] = None
             line["cpu_baseline"]["sample_4_threads"] = "failed: %s" % ex
+        del A_cpu
+    if need_host:
+        del A_host, A_pin
+    if not args.no_secondary:
+        line["secondary"] = secondary_records(L, args, local_rank, peak, peak_src)
     print(json.dumps(line), flush=True)
+    if line["parity"]["ok"] is False or line["parity"].get("cpu_prefix_ok") is False:
+        raise SystemExit("PARITY FAILURE: the run's pivot log / b column differ from the committed digests")
 
 
 def main():

@@ -189,6 +189,11 @@ int lps_shard_attach_ptrs(lps_handle h, void *const *comm_ptrs);
 int lps_device_info(lps_handle h, int *sm_count, int64_t *hbm_bytes, int *cc_major, int *cc_minor);
 int lps_tableau_bytes(lps_handle h, int64_t *bytes);     /* 8*(m+1)*pitch */
 int lps_algorithmic_bytes_per_pivot(lps_handle h, int64_t *bytes); /* 16*(m+1)*(n+1) */
+/* Measurement aid for the roofline of the blocked pass (no reference analogue): issue rate of the pass's
+   own instruction mix -- separately rounded DMUL + DADD on independent chains, 256 threads x 4 CTAs per SM --
+   in FP64 thread-instructions per second, timed with CUDA events on the handle's stream for about `ms`
+   milliseconds.  This is the FP64 roof the pass is held against beside the HBM one. */
+int lps_measure_fp64_issue_rate(lps_handle h, double ms, double *inst_per_s);
 
 #ifdef __cplusplus
 }

@@ -628,10 +628,12 @@ bool make_map(CUtensorMap* map, const double* base, unsigned long long inner, un
 // Shapes of the TMA pass the library is built with: <pending pivots held in registers, rows per thread per
 // stage, consumer warps> (SweepShape, lps_sweep.cuh).  pass_shape(): update_variant 10 / 11 / 12 pick one
 // explicitly (tuning), otherwise the default for the block size.
-using ShapeW12 = SweepShape<16, 4, 12>;   // 512 threads, 128 registers, three consumer warps per scheduler
-using ShapeW8 = SweepShape<16, 4, 8>;     // 384 threads, 168 registers, two consumer warps per scheduler
-using ShapeT8 = SweepShape<16, 8, 8>;     // ... with 8 rows per thread (16-row stages)
-using ShapeS8 = SweepShape<8, 4, 12>;     // small blocks (<= 8 pending pivots)
+// <pending pivots in registers, rows per thread per stage, columns per thread, consumer warps>
+using ShapeW12 = SweepShape<16, 4, 2, 12>;  // 512 threads, 128 registers, three consumer warps per scheduler
+using ShapeW8 = SweepShape<16, 2, 4, 8>;    // 384 threads, 168 registers, two consumer warps per scheduler, 4 columns per
+                                            // thread: half the shared-memory operand traffic per FP64 instruction
+using ShapeT8 = SweepShape<16, 4, 2, 8>;    // 384 threads, 168 registers, 2 columns per thread
+using ShapeS8 = SweepShape<8, 4, 4, 12>;    // small blocks (<= 8 pending pivots): 4 columns per thread fit 128 registers
 
 int pass_shape(lps_handle h) {
   if (h->block <= 8) return 3;
@@ -1052,6 +1054,23 @@ int run_blocked(lps_handle h, int64_t max_pivots, lps_run_result* res) {
     res->kernel_launches = launches;
   }
   return LPS_OK;
+}
+
+// FP64 issue-rate probe (the roof of the blocked pass beside HBM): the replay's instruction mix on independent
+// chains; the multiplier is another chain's running value, so nothing can be hoisted out of the loop
+template <int kChains>
+__global__ void __launch_bounds__(256, 4) k_fp64_probe(double* out, double r, int iters) {
+  double x[kChains];
+#pragma unroll
+  for (int c = 0; c < kChains; c++) x[c] = 1.0 + 1e-3 * (double)((threadIdx.x + c) & 63);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int c = 0; c < kChains; c++) x[c] = __dsub_rn(x[c], __dmul_rn(x[(c + 1) % kChains], r));
+  }
+  double s2 = 0;
+#pragma unroll
+  for (int c = 0; c < kChains; c++) s2 += x[c];
+  if (s2 == 12345.678) out[0] = s2;      // keeps the chains alive without a store per thread
 }
 
 }  // namespace
@@ -1640,6 +1659,27 @@ int lps_tableau_bytes(lps_handle h, int64_t* bytes) {
 int lps_algorithmic_bytes_per_pivot(lps_handle h, int64_t* bytes) {
   if (!h || !bytes || !h->loaded) return LPS_ERR_STATE;
   *bytes = 16ll * (h->m + 1) * (h->n + 1);
+  return LPS_OK;
+}
+
+int lps_measure_fp64_issue_rate(lps_handle h, double ms, double* inst_per_s) {
+  if (!h || !inst_per_s) return LPS_ERR_INVALID;
+  CK(cudaSetDevice(h->dev));
+  constexpr int kChains = 16;
+  const int grid = 4 * h->sm_count, threads = 256, iters = 2048;
+  double* out = reinterpret_cast<double*>(h->partials);
+  k_fp64_probe<kChains><<<grid, threads, 0, h->stream>>>(out, 0.5, 16);     // warm-up
+  const double per_launch = (double)grid * threads * iters * kChains * 2.0;
+  // about 0.15 ms per launch at 18 T inst/s: enough launches to fill `ms`
+  const int reps = std::max(1, std::min(4096, (int)(ms / 0.15)));
+  CK(cudaEventRecord(h->ev_begin, h->stream));
+  for (int k = 0; k < reps; k++) k_fp64_probe<kChains><<<grid, threads, 0, h->stream>>>(out, 0.5, iters);
+  CK(cudaEventRecord(h->ev_end, h->stream));
+  CK(cudaEventSynchronize(h->ev_end));
+  CK(cudaGetLastError());
+  float el = 0.f;
+  CK(cudaEventElapsedTime(&el, h->ev_begin, h->ev_end));
+  *inst_per_s = el > 0.f ? per_launch * reps / (el * 1e-3) : 0.0;
   return LPS_OK;
 }
 

@@ -254,6 +254,12 @@ class LPState:
             arr[k].kind, arr[k].index, arr[k].coef = int(kind), int(index), float(coef)
         self._ck(self._lib.lps_rebuild_objective(self._h, arr, len(ops)), "rebuild_objective")
 
+    def measure_fp64_issue_rate(self, ms: float = 100.0) -> float:
+        """FP64 thread-instructions per second of the pass's DMUL + DADD mix on this GPU (roofline aid)."""
+        x = c_double()
+        self._ck(self._lib.lps_measure_fp64_issue_rate(self._h, float(ms), byref(x)), "measure_fp64_issue_rate")
+        return x.value
+
     def algorithmic_bytes_per_pivot(self) -> int:
         x = c_int64()
         self._ck(self._lib.lps_algorithmic_bytes_per_pivot(self._h, byref(x)), "bytes")

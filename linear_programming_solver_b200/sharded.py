@@ -135,30 +135,34 @@ class ShardedLPState(LPState):
 
 
 # ---------------------------------------------------------------------------------------------
-def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_name, measured_peak, ClockSampler,
-                  roofline_block):
-    """bench.py's N > 1 arm: the same LP row-sharded over `world` GPUs (strong scaling)."""
+def bench_sharded(args, dist, rank, world, local_rank, B):
+    """bench.py's N > 1 arm: the same LP row-sharded over `world` GPUs (strong scaling).  `B` is the bench
+    module (helpers shared with the single-GPU arm: roofline record, clock sampler, digests)."""
     import json
 
     import torch
 
     m, n, P = args.m, args.n, args.pivots_per_step
-    st = ShardedLPState(m, n, rank, world, synthetic_seed=args.seed, device=local_rank, time_kernels=True,
-                        loop_mode=args.loop_mode, block_pivots=args.block)
+    kw = dict(loop_mode=args.loop_mode, block_pivots=args.block, panel_ctas=args.panel_ctas)
+    if args.variant >= 0:
+        kw["update_variant"] = args.variant
+    st = ShardedLPState(m, n, rank, world, synthetic_seed=args.seed, device=local_rank, time_kernels=True, **kw)
     st.attach_via(dist)
     bytes_pp_local = st.algorithmic_bytes_per_pivot()        # this rank's rows (+ objective replica)
     bytes_pp_global = 16 * (m + 1) * (n + 1)
+    mloc = st.row1 - st.row0
 
     def barrier():
         torch.cuda.synchronize()
         dist.barrier()
 
-    sampler = ClockSampler(local_rank)     # started before the warm-up: nvidia-smi takes a second to answer
+    sampler = B.ClockSampler(local_rank)     # started before the warm-up: nvidia-smi takes a second to answer
     sampler.start()
     if rank == 0:
         sampler.wait_first()
+    total = 0
     for _ in range(args.warmup):
-        st.run(P)
+        total += st.run(P).npivots
     barrier()
     sampler.mark()
     dev_ms, upd_ms, upd_n, launches, pivots = 0.0, 0.0, 0, 0, 0
@@ -173,16 +177,30 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
+    total += pivots
+    fp64_peak = st.measure_fp64_issue_rate(100.0)
     t = torch.tensor([dev_ms, upd_ms / max(upd_n, 1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, upd_avg_ms = float(t[0]), float(t[1])
     tl = torch.tensor([launches], dtype=torch.int64, device="cuda")
     dist.all_reduce(tl)
+    tf = torch.tensor([fp64_peak], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tf, op=dist.ReduceOp.MIN)
+
+    # parity: every rank holds the whole pivot log (it must be the same one) and its rows of b
+    logs = [None] * world
+    dist.all_gather_object(logs, B.digest_log(st.pivot_log))
+    b_global = st.gather_b(dist)
+    parity = None
+    if rank == 0:
+        parity = B.parity_block(m, n, args.seed, total, st.pivot_log, b_global)
+        parity["ranks_agree_on_the_log"] = bool(len(set(logs)) == 1)
+        if not parity["ranks_agree_on_the_log"]:
+            parity["ok"] = False
 
     # e2e: every rank loads ITS rows from pinned host memory, runs, reads its part of the result
     e2e = None
     if not args.no_e2e:
-        mloc = st.row1 - st.row0
         A_pin = torch.empty((mloc, n), dtype=torch.float64, pin_memory=True)
         A_host = A_pin.numpy()
         g = ShardedLPState(m, n, rank, world, synthetic_seed=args.seed, device=local_rank)
@@ -194,8 +212,7 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
         for _ in range(3):
             barrier()
             t0 = time.perf_counter()
-            s = ShardedLPState(m, n, rank, world, A_host, b_host, c_host, device=local_rank, loop_mode=args.loop_mode,
-                               block_pivots=args.block)
+            s = ShardedLPState(m, n, rank, world, A_host, b_host, c_host, device=local_rank, **kw)
             s.attach_via(dist)
             r2 = s.run(Pe)
             out = (s.b, s.c, s.v, s.positions)
@@ -206,38 +223,46 @@ def bench_sharded(args, dist, rank, world, local_rank, METRIC, UNIT, workload_na
             dist.barrier()
             s.close()
             best = float(tt[0]) if best is None else min(best, float(tt[0]))
-        e2e = {"value": Pe / best, "unit": UNIT, "h2d_bytes_per_step": int(8 * (m * n + m + world * n)),
+        e2e = {"value": Pe / best, "unit": B.UNIT, "h2d_bytes_per_step": int(8 * (m * n + m + world * n)),
                "d2h_bytes_per_step": int(8 * (m + world * (n + 1)) + 4 * world * (m + n)),
                "pivots_per_call": Pe, "seconds_per_call": best,
                "what": "per rank: shard load from pinned host memory + IPC attach + run(%d) + read b,c,v,positions" % Pe}
+    bad = False
     if rank == 0:
-        peak, peak_src = measured_peak()
+        peak, peak_src = B.measured_peak()
         value = pivots / (dev_ms_max / 1e3)
-        rl = roofline_block(bytes_pp_local, pivots, upd_avg_ms * max(upd_n, 1), upd_n,
-                            ("lps::ks_update (per rank)", "lps::kb_flush (per rank)"), peak, peak_src)
+        per_launch = round(pivots / max(upd_n, 1))
+        kernels = ("lps::ks_update (per rank)",
+                   "lps::kb_step (per rank; pass role: sweep_role)" if args.loop_mode in (0, 7) else "lps::kb_flush / kb_sweep (per rank)")
+        rl = B.roofline_block(bytes_pp_local, pivots, upd_avg_ms * max(upd_n, 1), upd_n, kernels, peak, peak_src,
+                              traffic=B.ncu_traffic("kb_step_n%d" % world if per_launch > 1 else "ks_update_n%d" % world),
+                              fp64_peak=float(tf[0]), cells=(mloc + 1) * (n + 1))
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(m, n), "pivots_per_step": P, "seed": args.seed,
-                       "loop": "blocked: %.1f pivots per tableau pass" % rl["pivots_per_launch"]
-                               if rl["pivots_per_launch"] > 1.5 else "one tableau pass per pivot",
-                       "sharding": "rows [k*m/G,(k+1)*m/G) per rank, objective row replicated",
-                       "exchange": "ratio candidates + scaled pivot row pushed into peer memory over NVLink "
-                                   "inside the kernels (no NCCL in the loop)",
-                       "l2": "per-rank shard (%.2f GB) is larger than the 126 MB L2" % (bytes_pp_local / 2e9),
-                       "timing": "CUDA events on each rank's stream, max over ranks"},
+            "config": B.config_block(m, n, args.seed),
+            "details": {"pivots_per_step": P, "loop": B.loop_name(rl, args.loop_mode),
+                        "sharding": "rows [k*m/G,(k+1)*m/G) per rank, objective row replicated",
+                        "exchange": "ratio candidates + scaled pivot row pushed into peer memory over NVLink "
+                                    "inside the kernels (no NCCL in the loop)",
+                        "l2": "per-rank shard (%.2f GB) is larger than the 126 MB L2" % (bytes_pp_local / 2e9),
+                        "timing": "CUDA events on each rank's stream, max over ranks"},
             "gpu_launches": int(tl[0]),
             "loop_gbs": bytes_pp_global * pivots / (dev_ms_max * 1e-3) / 1e9,
             "frac_of_8tbs_per_gpu": bytes_pp_global * pivots / (dev_ms_max * 1e-3) / 1e9 / 8000.0 / world,
             "loop_dram_gbs_per_gpu": bytes_pp_local * upd_n / (dev_ms_max * 1e-3) / 1e9,
             "wall_s": wall,
             "roofline": rl,
+            "parity": parity,
             "clocks": clocks,
         }
         if e2e:
             line["e2e"] = e2e
         print(json.dumps(line), flush=True)
+        bad = parity["ok"] is False
     st.close()
     dist.barrier()
     dist.destroy_process_group()
+    if bad:
+        raise SystemExit("PARITY FAILURE: the %d-rank run's pivot log / b column differ from the committed digests" % world)
