@@ -625,31 +625,36 @@ bool make_map(CUtensorMap* map, const double* base, unsigned long long inner, un
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Shapes of the TMA pass the library is built with: <pending pivots held in registers, rows per thread per
-// stage, consumer warps> (SweepShape, lps_sweep.cuh).  pass_shape(): update_variant 10 / 11 / 12 pick one
-// explicitly (tuning), otherwise the default for the block size.
-// <pending pivots in registers, rows per thread per stage, columns per thread, consumer warps>
-using ShapeW12 = SweepShape<16, 4, 2, 12>;  // 512 threads, 128 registers, three consumer warps per scheduler
-using ShapeW8 = SweepShape<16, 2, 4, 8>;    // 384 threads, 168 registers, two consumer warps per scheduler, 4 columns per
-                                            // thread: half the shared-memory operand traffic per FP64 instruction
-using ShapeT8 = SweepShape<16, 4, 2, 8>;    // 384 threads, 168 registers, 2 columns per thread
-using ShapeS8 = SweepShape<8, 4, 4, 12>;    // small blocks (<= 8 pending pivots): 4 columns per thread fit 128 registers
+// Shapes of the TMA pass the library is built with (SweepShape, lps_sweep.cuh):
+// <pending pivots in registers, rows per thread per sub-pass, columns per thread, consumer warps, warps across the
+//  strip, sub-passes per stage>.  pass_shape(): update_variant 10.. pick one explicitly (tuning), otherwise the
+// default for the block size.
+using ShapeA = SweepShape<16, 2, 2, 12, 4, 2>;   // 512 threads / 128 registers: 12 consumer warps, 256-column strips, 12-row stages
+using ShapeB = SweepShape<16, 2, 2, 15, 3, 2>;   // 512 threads / 128 registers: 15 consumer warps, 192-column strips, 20-row stages
+using ShapeC = SweepShape<16, 4, 2, 8, 4, 1>;    // 384 threads / 168 registers:  8 consumer warps, 256-column strips,  8-row stages
+using ShapeD = SweepShape<16, 4, 2, 8, 4, 2>;    // ... 16-row stages (two sub-passes per barrier round trip)
+using ShapeE = SweepShape<16, 4, 2, 8, 4, 1, true>;   // ... software-pipelined over two register sets
+using ShapeS = SweepShape<8, 4, 2, 12, 4, 1>;    // small blocks (<= 8 pending pivots)
 
 int pass_shape(lps_handle h) {
-  if (h->block <= 8) return 3;
+  if (h->block <= 8) return 5;
   switch (h->opt.update_variant) {
     case 11: return 1;
     case 12: return 2;
+    case 13: return 3;
+    case 14: return 4;
     default: return 0;
   }
 }
 #define LPS_WITH_SHAPE(h_, ...)                    \
   do {                                             \
     switch (pass_shape(h_)) {                      \
-      case 1: { using Shape = ShapeW8; __VA_ARGS__; } break;  \
-      case 2: { using Shape = ShapeT8; __VA_ARGS__; } break;  \
-      case 3: { using Shape = ShapeS8; __VA_ARGS__; } break;  \
-      default: { using Shape = ShapeW12; __VA_ARGS__; } break; \
+      case 1: { using Shape = ShapeB; __VA_ARGS__; } break;  \
+      case 2: { using Shape = ShapeC; __VA_ARGS__; } break;  \
+      case 3: { using Shape = ShapeD; __VA_ARGS__; } break;  \
+      case 4: { using Shape = ShapeE; __VA_ARGS__; } break;  \
+      case 5: { using Shape = ShapeS; __VA_ARGS__; } break;  \
+      default: { using Shape = ShapeA; __VA_ARGS__; } break; \
     }                                              \
   } while (0)
 
@@ -658,6 +663,7 @@ bool sweep_available(lps_handle h) {
   return h->block > 1 && h->block <= 16 && h->comm && h->acols && encode_fn() != nullptr;
 }
 int pass_stage_rows(lps_handle h) { int r = 0; LPS_WITH_SHAPE(h, r = Shape::kSR); return r; }
+int pass_cols(lps_handle h) { int r = 0; LPS_WITH_SHAPE(h, r = Shape::kCols); return r; }
 int pass_threads(lps_handle h) { int r = 0; LPS_WITH_SHAPE(h, r = Shape::kThreads); return r; }
 size_t pass_smem_bytes(lps_handle h) { size_t r = 0; LPS_WITH_SHAPE(h, r = Shape::kBytes); return r; }
 
@@ -669,7 +675,7 @@ size_t step_smem_bytes(lps_handle h) {
 int ensure_maps(lps_handle h, bool two) {
   const int want = two ? 2 : 1;
   if (h->tm_valid && h->tm_rows_set >= want) return LPS_OK;
-  const unsigned int bw = (unsigned int)std::min<long long>(kSwCols, h->ld);
+  const unsigned int bw = (unsigned int)std::min<long long>(pass_cols(h), h->ld);
   const unsigned int bu = (unsigned int)std::min(sweep_ks(h), h->block);
   const unsigned int sr = (unsigned int)pass_stage_rows(h);
   bool ok = make_map(&h->tm_T[0], h->T, h->ld, h->m + 1, h->ld, bw, sr);
@@ -700,7 +706,7 @@ int sweep_chunk_rows(lps_handle h, int ncta) {
   int cr = h->opt.pass_chunk_rows;
   if (cr <= 0) {
     // about two dozen chunks per CTA, so the tail of the pass (CTAs finishing at different times) stays small
-    const long long bw = std::min<long long>(kSwCols, h->ld);
+    const long long bw = std::min<long long>(pass_cols(h), h->ld);
     const long long nstrips = (h->ld + bw - 1) / bw;
     cr = (int)(((long long)(h->m + 1) * nstrips) / (24ll * std::max(1, ncta)));
     cr = std::min(cr, 240);
@@ -717,7 +723,7 @@ void fill_sweep_args(lps_handle h, SweepArgs& sw, int q, bool inplace, int cta0,
   sw.ld = h->ld;
   sw.rows = h->m + 1;
   sw.chunk_rows = sweep_chunk_rows(h, ncta);
-  sw.bw = (int)std::min<long long>(kSwCols, h->ld);
+  sw.bw = (int)std::min<long long>(pass_cols(h), h->ld);
   sw.bu = std::min(sweep_ks(h), h->block);
   sw.q = q;
   sw.inplace = inplace ? 1 : 0;

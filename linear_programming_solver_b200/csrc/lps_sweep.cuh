@@ -36,30 +36,37 @@
 
 namespace lps {
 
-constexpr int kSwCols = 256;                              // strip width (TMA box limit: 256 elements)
 constexpr unsigned long long kSwWaitNs = 4ull * 1000ull * 1000ull * 1000ull;
 
-// Shape of the pass: kS = most pending pivots (their rows live in registers), kR x kC = rows x columns
-// per consumer thread per stage (kC = 2 or 4), kCW = consumer warps: 256 / (32 kC) of them span the
-// columns of a strip, the rest are stacked over the rows of a stage.
-//   Every FP64 instruction needs one a_u[i] operand, and that operand reaches every lane through the
-//   shared-memory data pipe (8 bytes x 32 lanes = two wavefronts per value, broadcast or not); it is
-//   reused by the thread's kC columns, so the pipe carries 8 / (2 kC) bytes per FP64 instruction per
-//   lane: with kC = 2 the LSU is as busy as the FP64 pipe (measured: both stuck near 55-60 %), with
-//   kC = 4 half as busy — paid for with 2 kS kC registers for the pending rows.
-// The register file is handed out to CTAs in units of four warps, so 8 + 1 warps cost 12 warps' worth
-// of registers (168 per thread) and 12 + 1 cost 16 (128 per thread); the padding warps idle in the
-// pass and work in the panel role.
-template <int kS_, int kR_, int kC_, int kCW_>
+// Shape of the pass.
+//   kS    most pending pivots: their rows r_u live in the consumer threads' registers (2 kS kC of them)
+//   kR    rows per consumer thread per sub-pass;  kC  columns per thread (2, or 4 as two pairs 64 apart)
+//   kCW   consumer warps;  kColWarps of them side by side span the strip (kColWarps x 32 kC columns, at most
+//         256: one TMA box), the kCW / kColWarps "row lanes" are stacked over the rows
+//   kP    sub-passes per stage: a stage holds kP x (row lanes x kR) rows, and a warp works through its kP row
+//         groups one after the other under ONE full / empty barrier round trip
+// What drives the choice (ncu, profiles/r02_pass_shapes.md): every FP64 instruction needs one a_u[i] operand,
+// delivered to every lane through the shared-memory pipe and reused by the thread's kC columns; the per-stage
+// bookkeeping (barrier probe, tile load, stores) is a latency chain that only OTHER warps' arithmetic hides,
+// so the FP64 pipe wants three or four consumer warps per scheduler; and registers come in units of four
+// warps per CTA (12 warps: 168 per thread, 16 warps: 128) while spills are expensive here — next to 220 KB of
+// shared memory the L1 that would cache them is almost gone.
+//   kPipe software-pipelined consumer (kP == 1): the tile of stage s+1 is fetched into a second register set in
+//         the middle of stage s's arithmetic (its barrier probe is issued before the arithmetic starts), so the
+//         barrier / shared-memory latencies of the per-stage bookkeeping hide under the warp's OWN FP64 work
+template <int kS_, int kR_, int kC_, int kCW_, int kColWarps_, int kP_, bool kPipe_ = false>
 struct SweepShape {
-  static constexpr int kS = kS_, kR = kR_, kC = kC_, kCW = kCW_;
-  static constexpr int kColWarps = kSwCols / (32 * kC);      // warps side by side over the strip
+  static constexpr int kS = kS_, kR = kR_, kC = kC_, kCW = kCW_, kColWarps = kColWarps_, kP = kP_;
+  static constexpr bool kPipe = kPipe_;
+  static_assert(!kPipe || kP == 1, "the pipelined consumer handles one sub-pass per stage");
+  static constexpr int kCols = kColWarps * 32 * kC;          // strip width
   static constexpr int kRowLanes = kCW / kColWarps;
-  static constexpr int kSR = kR * kRowLanes;                 // rows per stage
-  static constexpr int kThreads = (kCW + 1 + 3) / 4 * 4 * 32;   // whole register-allocation units of four warps
-  static constexpr size_t kTile = (size_t)kSR * kSwCols * sizeof(double);
-  static constexpr size_t kASlice = (size_t)kS * kSR * sizeof(double);
-  static constexpr size_t kRSlice = (size_t)kS * kSwCols * sizeof(double);
+  static constexpr int kGR = kR * kRowLanes;                 // rows per sub-pass
+  static constexpr int kSR = kGR * kP;                       // rows per stage
+  static constexpr int kThreads = (kCW + 1 + 3) / 4 * 4 * 32;   // + the producer warp, in whole units of four warps
+  static constexpr size_t kTile = (size_t)kSR * kCols * sizeof(double);
+  static constexpr size_t kASlice = ((size_t)kS * kSR * sizeof(double) + 127) / 128 * 128;
+  static constexpr size_t kRSlice = (size_t)kS * kCols * sizeof(double);
   static constexpr size_t kBudget = 220 * 1024;
   static constexpr int kStagesFit = (int)((kBudget - 2 * kRSlice) / (kTile + kASlice));
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
@@ -71,9 +78,9 @@ struct SweepShape {
   static constexpr size_t kOffMeta = kOffBars + (2 * kStages + 4) * sizeof(unsigned long long);
   static constexpr size_t kOffScal = kOffMeta + 2 * 16;
   static constexpr size_t kBytes = kOffScal + (size_t)kS * (8 + 4 + 4) + 64;
-  static_assert((kC == 2 || kC == 4) && kCW % kColWarps == 0 && kR % 2 == 0, "shape");
+  static_assert((kC == 2 || kC == 4) && kCW % kColWarps == 0 && kR % 2 == 0 && kCols <= 256, "shape");
   static_assert(kStages >= 3, "pipeline depth");
-  static_assert(kASlice % 128 == 0 && kTile % 128 == 0, "TMA destinations are 128-byte aligned");
+  static_assert(kTile % 128 == 0 && kRSlice % 128 == 0 && (kSR * sizeof(double)) % 16 == 0, "TMA alignment");
 };
 
 // ---- mbarrier / TMA primitives (PTX ISA 8.x, sm_90+) ------------------------------------------
@@ -99,6 +106,18 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe (no suspend): has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test_wait(unsigned long long* bar, unsigned int parity) {
+  unsigned int ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
@@ -155,7 +174,7 @@ struct SweepArgs {
   long long ld;
   int rows;                    // mloc + 1 (objective row included)
   int chunk_rows;              // rows per chunk, a multiple of the stage height
-  int bw;                      // tile width in columns = min(256, ld): box of the T and pending-row maps
+  int bw;                      // tile width in columns = min(Shape::kCols, ld): box of the T and pending-row maps
   int bu;                      // pending pivots per box = min(kS, block_pivots)
   int q;                       // launch parity: the pass applies pending set q (ctl->blk_*2[q])
   int inplace;                 // 1: write back into the current buffer; 0: write the other one and publish the flip
@@ -169,8 +188,9 @@ template <class Shape>
 __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap* tmT0, const CUtensorMap* tmT1,
                                            const CUtensorMap* tmA, const CUtensorMap* tmR, unsigned char* smem) {
   using SM = Shape;
-  constexpr int kS = Shape::kS, kSwR = Shape::kR, kSwSR = Shape::kSR, kSwStages = Shape::kStages;
-  constexpr int kSwConsumerWarps = Shape::kCW;
+  constexpr int kS = Shape::kS, kR = Shape::kR, kC = Shape::kC, kH = kC / 2, kP = Shape::kP;
+  constexpr int kGR = Shape::kGR, kSR = Shape::kSR, kStages = Shape::kStages, kCW = Shape::kCW;
+  constexpr int kCols = Shape::kCols;
   CtlS* const ctl = a.ctl;
   const int set = a.q;
   const int t = ctl->blk_pend[set];
@@ -182,10 +202,10 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
   double* const s_a = reinterpret_cast<double*>(smem + SM::kOffA);
   double* const s_r = reinterpret_cast<double*>(smem + SM::kOffR);
   unsigned long long* const full = reinterpret_cast<unsigned long long*>(smem + SM::kOffBars);
-  unsigned long long* const empty = full + kSwStages;
-  unsigned long long* const r_full = empty + kSwStages;      // [2]
-  unsigned long long* const r_empty = r_full + 2;             // [2]
-  int4* const desc = reinterpret_cast<int4*>(smem + SM::kOffMeta);      // chunk descriptor {j0, first row, stages, stop}
+  unsigned long long* const empty = full + kStages;
+  unsigned long long* const r_full = empty + kStages;       // [2]
+  unsigned long long* const r_empty = r_full + 2;            // [2]
+  int4* const desc = reinterpret_cast<int4*>(smem + SM::kOffMeta);      // [2] chunk descriptor {j0, first row, stages, stop}
   double* const s_p = reinterpret_cast<double*>(smem + SM::kOffScal);
   int* const s_l = reinterpret_cast<int*>(s_p + kS);
   int* const s_e = s_l + kS;
@@ -198,13 +218,13 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
       s_p[tid] = ctl->blk_p2[set][tid];
     }
     if (tid == 0) {
-      for (int s = 0; s < kSwStages; s++) {
+      for (int s = 0; s < kStages; s++) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], kSwConsumerWarps);
+        mbar_init(&empty[s], kCW);
       }
       for (int b2 = 0; b2 < 2; b2++) {
         mbar_init(&r_full[b2], 1);
-        mbar_init(&r_empty[b2], kSwConsumerWarps);
+        mbar_init(&r_empty[b2], kCW);
       }
       mbar_fence_init();
     }
@@ -214,13 +234,13 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
     const int nstrips = (int)((a.ld + bw - 1) / bw);
     const int nbands = (a.rows + a.chunk_rows - 1) / a.chunk_rows;
     const long long nchunks = (long long)nstrips * nbands;
-    const unsigned int tile_bytes = (unsigned int)(kSwSR * bw * sizeof(double));
-    const unsigned int a_bytes = (unsigned int)(a.bu * kSwSR * sizeof(double));
+    const unsigned int tile_bytes = (unsigned int)(kSR * bw * sizeof(double));
+    const unsigned int a_bytes = (unsigned int)(a.bu * kSR * sizeof(double));
     const unsigned int r_bytes = (unsigned int)(a.bu * bw * sizeof(double));
 
-    if (warp > kSwConsumerWarps) {
+    if (warp > kCW) {
       // padding warps of the register-allocation unit: nothing to do in the pass
-    } else if (warp == kSwConsumerWarps) {
+    } else if (warp == kCW) {
       // ---------------- producer: one lane issues every bulk copy of this CTA ----------------
       // Per chunk: the chunk descriptor {j0, first row, stages, stop} and the chunk's slice of the pending
       // rows travel under the r_full / r_empty barrier pair; then one tile + a-slice per stage under the
@@ -246,36 +266,32 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
           const int j0 = (int)(c % nstrips) * bw;
           const int ib = (int)(c / nstrips) * a.chunk_rows;
           const int iend = min(ib + a.chunk_rows, a.rows);
-          desc[rb] = make_int4(j0, ib, (iend - ib + kSwSR - 1) / kSwSR, 0);
+          desc[rb] = make_int4(j0, ib, (iend - ib + kSR - 1) / kSR, 0);
           mbar_arrive_expect_tx(&r_full[rb], r_bytes);
-          tma_load_2d(s_r + (size_t)rb * kS * kSwCols, tmR, j0, 0, &r_full[rb]);
-          for (int i0 = ib; i0 < iend; i0 += kSwSR) {
+          tma_load_2d(s_r + (size_t)rb * kS * kCols, tmR, j0, 0, &r_full[rb]);
+          for (int i0 = ib; i0 < iend; i0 += kSR) {
             mbar_wait(&empty[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&full[stage], tile_bytes + a_bytes);
-            tma_load_2d_hint(tiles + (size_t)stage * kSwSR * kSwCols, tmT, j0, i0, &full[stage], pol);
-            tma_load_2d(s_a + (size_t)stage * kS * kSwSR, tmA, i0, 0, &full[stage]);
-            if (++stage == kSwStages) { stage = 0; phase ^= 1u; }
+            tma_load_2d_hint(tiles + (size_t)stage * kSR * kCols, tmT, j0, i0, &full[stage], pol);
+            tma_load_2d(smem + SM::kOffA + (size_t)stage * SM::kASlice, tmA, i0, 0, &full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     } else {
       // ---------------- consumers ----------------
-      constexpr int kC = Shape::kC, kH = kC / 2;          // kH column pairs per thread, 64 columns apart
       const int cgrp = warp % Shape::kColWarps, rlane = warp / Shape::kColWarps;
       const int wcol = cgrp * 32 * kC;                     // first column of my warp inside the strip
       const int jt = wcol + lane * 2;                      // my first pair; the second one (kC == 4) is 64 further
       // byte offsets of my cells inside a stage's tile / a-slice: fixed for the whole pass
-      const unsigned int tile_off = (unsigned int)(((rlane * kSwR) * bw + jt) * sizeof(double));
-      const unsigned int tiles_s = smem_u32(tiles) + tile_off;
-      const unsigned int sa_s = smem_u32(s_a) + (unsigned int)(rlane * kSwR * sizeof(double));
       const unsigned int row_b = (unsigned int)(bw * sizeof(double));
+      const unsigned int tiles_s = smem_u32(tiles) + (unsigned int)(rlane * kR) * row_b + (unsigned int)(jt * sizeof(double));
+      const unsigned int sa_s = smem_u32(s_a) + (unsigned int)(rlane * kR * sizeof(double));
       double r[kS][kC];
 #pragma unroll
       for (int u = 0; u < kS; u++)
 #pragma unroll
         for (int c = 0; c < kC; c++) r[u][c] = 0.0;
-      unsigned int colmask = 0;                          // pending pivots whose entering column my WARP holds
-      unsigned int rowmask = 0;                          // pending pivots whose leaving row lies in this chunk
       int stage = 0;
       unsigned int phase = 0;
       for (unsigned int nc = 0;; nc++) {
@@ -286,7 +302,7 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
         if (ds.w) break;
         const int j0 = ds.x, ib = ds.y;
         int nst = ds.z;
-        const double* const srb = s_r + (size_t)rb * kS * kSwCols;    // stays valid until I release it below
+        const double* const srb = s_r + (size_t)rb * kS * kCols;    // stays valid until I release it below
 #pragma unroll
         for (int h = 0; h < kH; h++) {
           if (jt + 64 * h < bw) {
@@ -299,7 +315,8 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
               }
           }
         }
-        colmask = rowmask = 0;
+        unsigned int colmask = 0;                        // pending pivots whose entering column my WARP holds
+        unsigned int rowmask = 0;                        // pending pivots whose leaving row lies in this chunk
         for (int u = 0; u < t; u++) {
           const int d = s_e[u] - (j0 + wcol);
           if (d >= 0 && d < 32 * kC) colmask |= 1u << u;
@@ -310,115 +327,224 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
         bool act[kH];
 #pragma unroll
         for (int h = 0; h < kH; h++) act[h] = (jt + 64 * h < bw) && (j + 64 * h < a.ld);
-        int i = ib + rlane * kSwR;                       // my first row of the stage
+        int i = ib + rlane * kR;                         // my first row of the stage's first sub-pass
         double* out = dst + (long long)i * a.ld + j;
-        // ---- the stages of the chunk ----
-        bool ready = mbar_try_wait(&full[stage], phase);
-        for (; nst > 0; nst--) {
-          if (!ready) mbar_wait(&full[stage], phase);
-          unsigned int smask = colmask;                  // ... or whose leaving row is one of my rows
-          if (rowmask != 0) {
-            for (int u = 0; u < t; u++) {
-              const int d = s_l[u] - i;
-              if (d >= 0 && d < kSwR) smask |= 1u << u;
-            }
-          }
-          const unsigned int tile = tiles_s + (unsigned int)stage * (unsigned int)(kSwSR * kSwCols * sizeof(double));
-          const unsigned int sa = sa_s + (unsigned int)stage * (unsigned int)(kS * kSwSR * sizeof(double));
-          double2 x[kSwR][kH];
+        if constexpr (Shape::kPipe) {
+          // ---- the stages of the chunk, software-pipelined over two register sets ----
+          auto load_x = [&](double2 (&x)[kR][kH], int st) {
+            const unsigned int tile = tiles_s + (unsigned int)st * (unsigned int)SM::kTile;
 #pragma unroll
-          for (int k = 0; k < kSwR; k++)
+            for (int k = 0; k < kR; k++)
 #pragma unroll
-            for (int h = 0; h < kH; h++) x[k][h] = lds128(tile + k * row_b + 64 * h * (unsigned int)sizeof(double));
-          // one pending pivot on my kSwR x kC cells: a_u[i..i+kSwR) from shared memory (warp-wide broadcasts)
-          auto load_a = [&](int u, double (&av)[kSwR]) {
-#pragma unroll
-            for (int k = 0; k < kSwR; k += 2) {
-              const double2 v = lds128(sa + (unsigned int)((u * kSwSR + k) * sizeof(double)));
-              av[k] = v.x;
-              av[k + 1] = v.y;
-            }
+              for (int h = 0; h < kH; h++) x[k][h] = lds128(tile + k * row_b + 64 * h * (unsigned int)sizeof(double));
           };
-          auto update = [&](int u, const double (&av)[kSwR]) {
-#pragma unroll
-            for (int k = 0; k < kSwR; k++)
-#pragma unroll
-              for (int h = 0; h < kH; h++) {
-                x[k][h].x = __dsub_rn(x[k][h].x, __dmul_rn(av[k], r[u][2 * h]));      // LPState.java:162-164 / :177
-                x[k][h].y = __dsub_rn(x[k][h].y, __dmul_rn(av[k], r[u][2 * h + 1]));
+          auto step = [&](double2 (&x)[kR][kH], double2 (&xn)[kR][kH], bool has_next) {
+            const int cs = stage;                          // the stage this step consumes
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            const bool nready = has_next ? mbar_test_wait(&full[stage], phase) : true;   // answer needed mid-arithmetic
+            const unsigned int sa = sa_s + (unsigned int)cs * (unsigned int)SM::kASlice;
+            unsigned int smask = colmask;
+            if (rowmask != 0) {
+              for (int u = 0; u < t; u++) {
+                const int d = s_l[u] - i;
+                if (d >= 0 && d < kR) smask |= 1u << u;
               }
-          };
-          if (smask == 0 && t == kS) {
-            // the common case, free of branches: the operands of pivot u + 1 are fetched while pivot u is applied
-            if constexpr (Shape::kThreads >= 512) {
-              // 128 registers per thread: one operand buffer (the other two warps of the scheduler cover the
-              // shared-memory latency); the second buffer cost spills of the loop state
+            }
+            auto load_a = [&](int u, double (&av)[kR]) {
 #pragma unroll
-              for (int u = 0; u < kS; u++) {
-                double av[kSwR];
+              for (int k = 0; k < kR; k += 2) {
+                const double2 v = lds128(sa + (unsigned int)((u * kSR + k) * sizeof(double)));
+                av[k] = v.x;
+                av[k + 1] = v.y;
+              }
+            };
+            auto update = [&](int u, const double (&av)[kR]) {
+#pragma unroll
+              for (int k = 0; k < kR; k++)
+#pragma unroll
+                for (int h = 0; h < kH; h++) {
+                  x[k][h].x = __dsub_rn(x[k][h].x, __dmul_rn(av[k], r[u][2 * h]));      // LPState.java:162-164 / :177
+                  x[k][h].y = __dsub_rn(x[k][h].y, __dmul_rn(av[k], r[u][2 * h + 1]));
+                }
+            };
+            auto fetch_next = [&]() {
+              if (has_next) {
+                if (!nready) mbar_wait(&full[stage], phase);
+                load_x(xn, stage);
+              }
+            };
+            if (smask == 0 && t == kS) {
+#pragma unroll
+              for (int u = 0; u < kS / 2; u++) {
+                double av[kR];
+                load_a(u, av);
+                update(u, av);
+              }
+              fetch_next();                                // lands while the second half is computed
+#pragma unroll
+              for (int u = kS / 2; u < kS; u++) {
+                double av[kR];
                 load_a(u, av);
                 update(u, av);
               }
             } else {
-              double a0[kSwR], a1[kSwR];
-              load_a(0, a0);
-#pragma unroll
-              for (int u = 0; u < kS; u += 2) {
-                load_a(u + 1, a1);
-                update(u, a0);
-                if (u + 2 < kS) load_a(u + 2, a0);
-                update(u + 1, a1);
-              }
-            }
-          } else {
-            // a partial block, or a pending pivot OVERWRITES some of my warp's cells in this stage (its leaving
-            // row is one of my rows / its entering column one of my warp's): rare, so a compact rolled loop
-            // that takes r_u from the chunk's shared-memory slice instead of the register copy — same values,
-            // same operations in the same order
-            for (int u = 0; u < t; u++) {
-              double av[kSwR];
-              load_a(u, av);
-              double rv[kC];
-#pragma unroll
-              for (int h = 0; h < kH; h++) {
-                const double2 v = act[h] ? *reinterpret_cast<const double2*>(srb + (size_t)u * bw + jt + 64 * h)
-                                         : make_double2(0.0, 0.0);
-                rv[2 * h] = v.x;
-                rv[2 * h + 1] = v.y;
-              }
-              const bool hit = (smask >> u) & 1u;
-              const int lk = hit ? s_l[u] - i : -1;      // its leaving row among my rows (else out of 0..kSwR-1)
-              const int ce = hit ? s_e[u] - j : -1;      // its entering column among mine: 0, 1 (, 64, 65)
-              const double pu = s_p[u];
-#pragma unroll
-              for (int k = 0; k < kSwR; k++) {
+              for (int u = 0; u < t; u++) {              // see the rolled loop of the plain consumer below
+                double av[kR];
+                load_a(u, av);
+                double rv[kC];
 #pragma unroll
                 for (int h = 0; h < kH; h++) {
-                  if (k == lk) {                         // LPState.java:137-146
-                    x[k][h].x = rv[2 * h];
-                    x[k][h].y = rv[2 * h + 1];
-                  } else {
-                    const double q = (ce == 64 * h || ce == 64 * h + 1) ? -ddiv_call(av[k], pu) : 0.0;   // :157 / :172
-                    x[k][h].x = (ce == 64 * h) ? q : __dsub_rn(x[k][h].x, __dmul_rn(av[k], rv[2 * h]));  // :162-164 / :177
-                    x[k][h].y = (ce == 64 * h + 1) ? q : __dsub_rn(x[k][h].y, __dmul_rn(av[k], rv[2 * h + 1]));
+                  const double2 v = act[h] ? *reinterpret_cast<const double2*>(srb + (size_t)u * bw + jt + 64 * h)
+                                           : make_double2(0.0, 0.0);
+                  rv[2 * h] = v.x;
+                  rv[2 * h + 1] = v.y;
+                }
+                const bool hit = (smask >> u) & 1u;
+                const int lk = hit ? s_l[u] - i : -1;
+                const int ce = hit ? s_e[u] - j : -1;
+                const double pu = s_p[u];
+#pragma unroll
+                for (int k = 0; k < kR; k++) {
+#pragma unroll
+                  for (int h = 0; h < kH; h++) {
+                    if (k == lk) {                       // LPState.java:137-146
+                      x[k][h].x = rv[2 * h];
+                      x[k][h].y = rv[2 * h + 1];
+                    } else {
+                      const double q = (ce == 64 * h || ce == 64 * h + 1) ? -ddiv_call(av[k], pu) : 0.0;   // :157 / :172
+                      x[k][h].x = (ce == 64 * h) ? q : __dsub_rn(x[k][h].x, __dmul_rn(av[k], rv[2 * h]));
+                      x[k][h].y = (ce == 64 * h + 1) ? q : __dsub_rn(x[k][h].y, __dmul_rn(av[k], rv[2 * h + 1]));
+                    }
+                  }
+                }
+              }
+              fetch_next();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[cs]);        // the a-slice of the stage is consumed (the tile long since)
+#pragma unroll
+            for (int k = 0; k < kR; k++)
+              if (i + k < a.rows) {
+#pragma unroll
+                for (int h = 0; h < kH; h++)
+                  if (act[h]) st128_stream(out + (long long)k * a.ld + 64 * h, x[k][h].x, x[k][h].y);
+              }
+            i += kSR;
+            out += (long long)kSR * a.ld;
+          };
+          double2 xa[kR][kH], xb[kR][kH];
+          mbar_wait(&full[stage], phase);
+          load_x(xa, stage);
+          while (nst > 0) {
+            step(xa, xb, nst > 1);
+            if (--nst == 0) break;
+            step(xb, xa, nst > 1);
+            --nst;
+          }
+        } else {
+        // ---- the stages of the chunk ----
+        bool ready = mbar_try_wait(&full[stage], phase);
+        for (; nst > 0; nst--) {
+          if (!ready) mbar_wait(&full[stage], phase);
+          const unsigned int tile0 = tiles_s + (unsigned int)stage * (unsigned int)SM::kTile;
+          const unsigned int sa0 = sa_s + (unsigned int)stage * (unsigned int)SM::kASlice;
+#pragma unroll
+          for (int p = 0; p < kP; p++) {
+            // my kR rows of sub-pass p: rows i + p kGR .. of the tableau, rows (p kRowLanes + rlane) kR .. of the tile
+            const int ip = i + p * kGR;
+            const unsigned int tile = tile0 + (unsigned int)(p * kGR) * row_b;
+            const unsigned int sa = sa0 + (unsigned int)(p * kGR * sizeof(double));
+            unsigned int smask = colmask;                // ... or whose leaving row is one of my rows
+            if (rowmask != 0) {
+              for (int u = 0; u < t; u++) {
+                const int d = s_l[u] - ip;
+                if (d >= 0 && d < kR) smask |= 1u << u;
+              }
+            }
+            double2 x[kR][kH];
+#pragma unroll
+            for (int k = 0; k < kR; k++)
+#pragma unroll
+              for (int h = 0; h < kH; h++) x[k][h] = lds128(tile + k * row_b + 64 * h * (unsigned int)sizeof(double));
+            // one pending pivot on my kR x kC cells: a_u[ip..ip+kR) from shared memory (warp-wide broadcasts)
+            auto load_a = [&](int u, double (&av)[kR]) {
+#pragma unroll
+              for (int k = 0; k < kR; k += 2) {
+                const double2 v = lds128(sa + (unsigned int)((u * kSR + k) * sizeof(double)));
+                av[k] = v.x;
+                av[k + 1] = v.y;
+              }
+            };
+            auto update = [&](int u, const double (&av)[kR]) {
+#pragma unroll
+              for (int k = 0; k < kR; k++)
+#pragma unroll
+                for (int h = 0; h < kH; h++) {
+                  x[k][h].x = __dsub_rn(x[k][h].x, __dmul_rn(av[k], r[u][2 * h]));      // LPState.java:162-164 / :177
+                  x[k][h].y = __dsub_rn(x[k][h].y, __dmul_rn(av[k], r[u][2 * h + 1]));
+                }
+            };
+            if (smask == 0 && t == kS) {
+              // the common case, free of branches
+#pragma unroll
+              for (int u = 0; u < kS; u++) {
+                double av[kR];
+                load_a(u, av);
+                update(u, av);
+              }
+            } else {
+              // a partial block, or a pending pivot OVERWRITES some of my warp's cells in this sub-pass (its
+              // leaving row is one of my rows / its entering column one of my warp's): rare, so a compact rolled
+              // loop that takes r_u from the chunk's shared-memory slice instead of the register copy — same
+              // values, same operations in the same order
+              for (int u = 0; u < t; u++) {
+                double av[kR];
+                load_a(u, av);
+                double rv[kC];
+#pragma unroll
+                for (int h = 0; h < kH; h++) {
+                  const double2 v = act[h] ? *reinterpret_cast<const double2*>(srb + (size_t)u * bw + jt + 64 * h)
+                                           : make_double2(0.0, 0.0);
+                  rv[2 * h] = v.x;
+                  rv[2 * h + 1] = v.y;
+                }
+                const bool hit = (smask >> u) & 1u;
+                const int lk = hit ? s_l[u] - ip : -1;   // its leaving row among my rows (else out of 0..kR-1)
+                const int ce = hit ? s_e[u] - j : -1;    // its entering column among mine: 0, 1 (, 64, 65)
+                const double pu = s_p[u];
+#pragma unroll
+                for (int k = 0; k < kR; k++) {
+#pragma unroll
+                  for (int h = 0; h < kH; h++) {
+                    if (k == lk) {                       // LPState.java:137-146
+                      x[k][h].x = rv[2 * h];
+                      x[k][h].y = rv[2 * h + 1];
+                    } else {
+                      const double q = (ce == 64 * h || ce == 64 * h + 1) ? -ddiv_call(av[k], pu) : 0.0;   // :157 / :172
+                      x[k][h].x = (ce == 64 * h) ? q : __dsub_rn(x[k][h].x, __dmul_rn(av[k], rv[2 * h]));  // :162-164 / :177
+                      x[k][h].y = (ce == 64 * h + 1) ? q : __dsub_rn(x[k][h].y, __dmul_rn(av[k], rv[2 * h + 1]));
+                    }
                   }
                 }
               }
             }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[stage]);     // the tile and its a-slice are consumed
-          if (++stage == kSwStages) { stage = 0; phase ^= 1u; }
-          if (nst > 1) ready = mbar_try_wait(&full[stage], phase);   // the probe overlaps the stores
-#pragma unroll
-          for (int k = 0; k < kSwR; k++)
-            if (i + k < a.rows) {
-#pragma unroll
-              for (int h = 0; h < kH; h++)
-                if (act[h]) st128_stream(out + (long long)k * a.ld + 64 * h, x[k][h].x, x[k][h].y);
+            if (p == kP - 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty[stage]);   // the tile and its a-slice are consumed
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              if (nst > 1) ready = mbar_try_wait(&full[stage], phase);   // the probe overlaps the stores
             }
-          i += kSwSR;
-          out += (long long)kSwSR * a.ld;
+#pragma unroll
+            for (int k = 0; k < kR; k++)
+              if (ip + k < a.rows) {
+#pragma unroll
+                for (int h = 0; h < kH; h++)
+                  if (act[h]) st128_stream(out + (long long)(p * kGR + k) * a.ld + 64 * h, x[k][h].x, x[k][h].y);
+              }
+          }
+          i += kSR;
+          out += (long long)kSR * a.ld;
+        }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&r_empty[rb]);        // the slice (and its descriptor slot) may be refilled

@@ -51,10 +51,10 @@ def test_blocked_bit_exact_vs_tier_f(m, n, seed, block, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12, 13, 14])
 def test_blocked_flush_variants(variant, mode):
     """every tile shape of the pass kernel gives the same bits (wide and tall cases, capped); 0-7 are the
-    cp.async kernel kb_flush (loop modes 5 and 6), 10-12 the shapes of the TMA pass"""
+    cp.async kernel kb_flush (loop modes 5 and 6), 10-14 the shapes of the TMA pass (14: producer folded into a consumer warp)"""
     L = _L()
     from linear_programming_solver_b200.lp_state import LPState
     for (m, n, seed, cap) in [(700, 5001, 2, 90), (2100, 530, 3, 70)]:
