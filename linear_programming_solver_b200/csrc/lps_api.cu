@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -484,14 +485,14 @@ int launch_flush_t(lps_handle h) {
     h->flush_grid = h->sm_count;   // persistent: one CTA per SM
   }
   kern<<<h->flush_grid, kFlushThreads * kLanes, smem, h->stream>>>(h->ctls, h->T, h->ld, h->m, h->acols, h->apitch,
-                                                                 h->peers.rowbuf[h->rank]);
+                                                                 h->peers.rowbuf[h->rank], h->block);
   return LPS_OK;
 }
 
 int launch_flush(lps_handle h) {
-  // default (and update_variant >= 10): the TMA pipeline of lps_sweep.cuh, in place; update_variant 0..9 select the cp.async kernel
+  // update_variant >= 10: the TMA pipeline of lps_sweep.cuh, in place; otherwise the cp.async kernel
   // kb_flush<128-thread row-group lanes per CTA, rows per group, groups per lane per chunk, L2 prefetch of the next group>
-  if ((h->opt.update_variant < 0 || h->opt.update_variant >= 10) && sweep_available(h)) return launch_sweep(h);
+  if (h->opt.update_variant >= 10 && sweep_available(h)) return launch_sweep(h);
   switch (h->opt.update_variant) {
     default: {
       // chunk height: 256 rows is the best of the B200 sweep (profiles/) while every CTA still gets a
@@ -639,11 +640,11 @@ using ShapeS = SweepShape<8, 4, 2, 12, 4, 1>;    // small blocks (<= 8 pending p
 int pass_shape(lps_handle h) {
   if (h->block <= 8) return 5;
   switch (h->opt.update_variant) {
+    case 10: return 0;
     case 11: return 1;
     case 12: return 2;
-    case 13: return 3;
     case 14: return 4;
-    default: return 0;
+    default: return 3;   // ShapeD: the fastest of the B200 sweep (profiles/r02_pass_shapes.md)
   }
 }
 #define LPS_WITH_SHAPE(h_, ...)                    \
@@ -748,6 +749,22 @@ int launch_sweep(lps_handle h) {
   return LPS_OK;
 }
 
+// look-ahead step with the cp.async pass (flush_role): chunk height as launch_flush picks it
+int step_flush_kg(lps_handle h, int ncta) {
+  const long long strips = (h->ld + kStripCols - 1) / kStripCols;
+  const long long per_cta_256 = strips * ((h->m + 256) / 256) / std::max(1, ncta);
+  if (per_cta_256 < 12) return 4;
+  if (per_cta_256 < 40) return 8;
+  return 16;
+}
+// the look-ahead loop's pass role: the cp.async kernel by default (the faster one on B200 so far,
+// profiles/r02_pass_shapes.md); update_variant >= 10 selects a shape of the TMA pipeline
+bool step_uses_flush(lps_handle h) { return h->opt.update_variant <= 9; }
+size_t step_flush_smem(lps_handle h, int kg) {
+  const size_t pass = (size_t)h->block * 2 * (kStripCols + 4 * 4 * kg) * sizeof(double);
+  return std::max(pass, (size_t)kLookMax * 512 * sizeof(double));
+}
+
 bool use_look(lps_handle h) {
   if (!sweep_available(h)) return false;
   if (h->opt.loop_mode == 7) return true;
@@ -757,10 +774,23 @@ bool use_look(lps_handle h) {
 int look_panel_ctas(lps_handle h) {
   int P = h->opt.panel_ctas;
   if (P <= 0) {
-    // the panel is a latency chain with O((m + n) * pending) of L2 traffic per pivot: a handful of SMs hide it
-    // behind a multi-GB pass; a small shard's pass is short, so its panel gets more
-    const double bytes = shard_bytes(h);
-    P = bytes > 3e9 ? 8 : bytes > 1.2e9 ? 12 : 16;
+    // Both roles are throughput-bound on the SMs they get: the pass needs ~0.37 ms per GB of shard on the whole
+    // GPU (16 pivots replayed, FP64 / issue-bound), a panel pivot ~6.5 us per trip of its CTAs over the local rows
+    // and (on the owner of the leaving row) over the columns, plus ~10 us of syncs and exchange (measured,
+    // profiles/r02_summary.md).  Pick the split that minimises the slower of the two.
+    const double pass_ms_full = 0.37 * shard_bytes(h) / 1e9 * h->block / 16.0 + 0.02;
+    const long long rows = (h->sharded ? h->m_total / h->world : h->m) + 1;
+    const int nt = step_uses_flush(h) ? 512 : pass_threads(h);
+    double best = 1e30;
+    P = 8;
+    for (int p = 2; p <= h->sm_count / 2; p++) {
+      const double trips = (double)((rows + (long long)nt * p - 1) / ((long long)nt * p)) +
+                           (double)((h->ld + (long long)nt * p - 1) / ((long long)nt * p));
+      const double panel_ms = h->block * (6.5 * trips + 10.0) * 1e-3;
+      const double pass_ms = pass_ms_full * h->sm_count / (double)(h->sm_count - p);
+      const double step = std::max(panel_ms, pass_ms);
+      if (step < best) { best = step; P = p; }
+    }
   }
   return std::max(1, std::min(P, h->sm_count - 1));
 }
@@ -800,6 +830,12 @@ int ensure_look(lps_handle h) {
   }
   int rc = ensure_maps(h, true);
   if (rc) return rc;
+  if (h->step_grid == 0 && step_uses_flush(h)) {
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->dev));
+    if (!coop) return fail(h, LPS_ERR_STATE, "device does not support cooperative launch");
+    h->step_grid = h->sm_count;     // the attribute is set per launch (the instantiation depends on the shape)
+  }
   if (h->step_grid == 0) {
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->dev));
@@ -844,6 +880,17 @@ int launch_step(lps_handle h) {
   h->panel_launches += 1;
   sa.tag0 = h->panel_launches * 64u;
   h->look_launches += 1;
+  if (step_uses_flush(h)) {
+    const int kg = step_flush_kg(h, h->step_grid - P);
+    const size_t smem = step_flush_smem(h, kg);
+    const void* ffn;
+    if (h->sharded) ffn = kg == 16 ? (const void*)kb_step_flush<true, 4, 4, 16, true> : kg == 8 ? (const void*)kb_step_flush<true, 4, 4, 8, true> : (const void*)kb_step_flush<true, 4, 4, 4, true>;
+    else ffn = kg == 16 ? (const void*)kb_step_flush<false, 4, 4, 16, true> : kg == 8 ? (const void*)kb_step_flush<false, 4, 4, 8, true> : (const void*)kb_step_flush<false, 4, 4, 4, true>;
+    CK(cudaFuncSetAttribute(ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* fargs[] = {&sa};
+    CK(cudaLaunchCooperativeKernel(ffn, dim3(h->step_grid), dim3(4 * kFlushThreads), fargs, smem, h->stream));
+    return LPS_OK;
+  }
   void* args[] = {&sa, &h->tm_T[0], &h->tm_T[1], &h->tm_A[q], &h->tm_R[q]};
   const void* fn = nullptr;
   if (h->sharded) LPS_WITH_SHAPE(h, fn = (const void*)kb_step<true, Shape>);
@@ -918,6 +965,15 @@ int run_look(lps_handle h, int64_t max_pivots, lps_run_result* res) {
     h->total_pivots = h->h_ctl->npivots;
     if (remaining >= 0) remaining -= done_now;
     if (h->h_ctl->status != kRunning && (h->h_ctls->blk_pend[0] | h->h_ctls->blk_pend[1]) == 0) break;
+  }
+  if (const char* dbg = std::getenv("LPS_DEBUG")) {
+    if (dbg[0] == '1') {
+      const unsigned long long* d = h->h_ctls->dbg_ns;
+      std::fprintf(stderr, "lps look-ahead run: rank %d  panel role: %.1f us per pivot over %llu pivots (%d CTAs); "
+                           "%lld launches, %lld with a pass\n",
+                   h->rank, d[15] ? 1e-3 * (double)d[14] / (double)d[15] : 0.0, d[15], look_panel_ctas(h), launches,
+                   upd_launches);
+    }
   }
   // the tableau may have ended up in the second buffer: make it the handle's current one
   if (h->h_ctls->cur_at[h->look_launches & 1u] == 1) {

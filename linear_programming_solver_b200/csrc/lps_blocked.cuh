@@ -876,27 +876,52 @@ constexpr int kFlushThreads = 128;
 constexpr int kStripCols = 4 * kFlushThreads;
 
 
+// The pass as a role: CTAs that call it (ncta of them) apply pending set `set` to the tableau Tsrc -> Tdst
+// (the same buffer for an in-place pass).  Acols / Rrows: the set's pending columns / rows.  `smem`: the CTA's
+// dynamic shared memory, 2 t (512 + kCH) doubles.  The last CTA retires the set (see sweep_role in lps_sweep.cuh:
+// same protocol, so the two pass kernels are interchangeable inside kb_step).
+struct FlushArgs {
+  CtlS* ctl;
+  double* Tbuf[2];
+  long long ld;
+  int mloc;
+  const double* Acols;     // [2][block][apitch]
+  long long apitch;
+  const double* Rrows;     // [2][block][ld]  (this rank's copy)
+  int block;
+  int q;                   // launch parity = pending set
+  int inplace;
+  int ncta;
+};
+
 template <int kLanes, int kU, int kG, bool kPre>   // kPre: prefetch the lane's next group of rows into L2
-__global__ void __launch_bounds__(kFlushThreads * kLanes, 1)
-kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double* __restrict__ Acols,
-         long long apitch, const double* __restrict__ Rrows) {
+__device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
   constexpr int kThreads = kFlushThreads * kLanes;
   constexpr int kCH = kU * kLanes * kG;            // rows per chunk
   static_assert(kU % 2 == 0, "16-byte copies of the pending columns");
-  const int t = ctl->blk_pend[0];
-  if (t == 0) return;
-  extern __shared__ __align__(32) double smem[];
+  CtlS* const ctl = fa.ctl;
+  const int set = fa.q;
+  const int t = ctl->blk_pend[set];
+  const int cur = ctl->cur_at[fa.q];
+  const double* const Ts = fa.Tbuf[cur];
+  double* const T = fa.Tbuf[fa.inplace ? cur : (cur ^ 1)];
+  const long long ld = fa.ld;
+  const int mloc = fa.mloc;
+  const long long apitch = fa.apitch;
+  const double* const Acols = fa.Acols + (size_t)set * fa.block * apitch;
+  const double* const Rrows = fa.Rrows + (size_t)set * fa.block * ld;
+  __shared__ bool s_last;
+  if (t > 0) {
   double* const s_r = smem;                                      // [2][t][kStripCols]
   double* const s_a = smem + (size_t)2 * t * kStripCols;         // [2][t][kCH]
   __shared__ double s_p[kMaxBlock];
   __shared__ int s_l[kMaxBlock], s_e[kMaxBlock];
   __shared__ long long s_claim[2];
-  __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid / kFlushThreads, ltid = tid % kFlushThreads;
   if (tid < t) {
-    s_l[tid] = ctl->blk_l2[0][tid];
-    s_e[tid] = ctl->blk_e2[0][tid];
-    s_p[tid] = ctl->blk_p2[0][tid];
+    s_l[tid] = ctl->blk_l2[set][tid];
+    s_e[tid] = ctl->blk_e2[set][tid];
+    s_p[tid] = ctl->blk_p2[set][tid];
   }
   const int nstrips = (int)((ld + kStripCols - 1) / kStripCols);
   const int nrb = (mloc + 1 + kCH - 1) / kCH;                    // chunks per strip
@@ -961,7 +986,8 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
           if (last) rmask |= 1u << u;
         }
       }
-      double* base = T + j0;
+      double* base = T + j0;               // stores
+      const double* sbase = Ts + j0;       // loads (the same buffer unless the pass runs out of place)
       auto rvec = [&](int u) {
         const double2 lo = *reinterpret_cast<const double2*>(sr + u * kStripCols);
         const double2 hi = *reinterpret_cast<const double2*>(sr + u * kStripCols + kStripCols / 2);
@@ -972,7 +998,7 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
       auto load_group = [&](D4 (&x)[kU], int i) {
 #pragma unroll
         for (int k = 0; k < kU; k++)
-          if (i + k < i_end) x[k] = ld256(base + (long long)(i + k) * ld);
+          if (i + k < i_end) x[k] = ld256(sbase + (long long)(i + k) * ld);
           else x[k].x = x[k].y = x[k].z = x[k].w = 0.0;
       };
       // replay the pending pivots on one group of rows held in registers, then store it
@@ -1076,11 +1102,11 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
           if (kPre) {
             const int in = i + kLanes * kU;
             if (g + kLanes < kCH / kU && in < i_end) {
-              prefetch_rows(base, in, i_end);
+              prefetch_rows(sbase, in, i_end);
             } else if (nxt < nchunks) {
               const long long j0n = (nxt % nstrips) * kStripCols + 4 * ltid;
               const int i0n = (int)(nxt / nstrips) * kCH;
-              if (j0n < ld) prefetch_rows(T + j0n, i0n + lane * kU, min(i0n + kCH, mloc + 1));
+              if (j0n < ld) prefetch_rows(Ts + j0n, i0n + lane * kU, min(i0n + kCH, mloc + 1));
             }
           }
           finish_group(x, i, g);
@@ -1090,19 +1116,46 @@ kb_flush(CtlS* ctl, double* __restrict__ T, long long ld, int mloc, const double
     cur = nxt;
     buf ^= 1;
   }
-  // last CTA of the grid retires the block
+  }
+  // last pass CTA retires the block
   __syncthreads();
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     __threadfence();
     unsigned int tk = atomicAdd(&ctl->blk_ticket, 1u);
-    s_last = (tk == gridDim.x - 1);
+    s_last = (tk == (unsigned int)fa.ncta - 1);
   }
   __syncthreads();
-  if (s_last && tid == 0) {
+  if (s_last && threadIdx.x == 0) {
     ctl->blk_ticket = 0;
     ctl->blk_queue = 0;
-    ctl->blk_pend[0] = 0;
+    ctl->blk_pend[set] = 0;
+    ctl->cur_at[fa.q ^ 1] = (!fa.inplace && t > 0) ? (cur ^ 1) : cur;   // read by the NEXT launch only
+    if (t > 0) ctl->sweeps_done += 1;
+    __threadfence();
   }
 }
+
+// the pass as a kernel of its own, in place on set 0 (loop modes 5 and 6)
+template <int kLanes, int kU, int kG, bool kPre>
+__global__ void __launch_bounds__(kFlushThreads * kLanes, 1)
+kb_flush(CtlS* ctl, double* T, long long ld, int mloc, const double* Acols, long long apitch, const double* Rrows,
+         int block) {
+  extern __shared__ __align__(32) double flush_smem[];
+  FlushArgs fa;
+  fa.ctl = ctl;
+  fa.Tbuf[0] = fa.Tbuf[1] = T;
+  fa.ld = ld;
+  fa.mloc = mloc;
+  fa.Acols = Acols;
+  fa.apitch = apitch;
+  fa.Rrows = Rrows;
+  fa.block = block;
+  fa.q = 0;
+  fa.inplace = 1;
+  fa.ncta = (int)gridDim.x;
+  flush_role<kLanes, kU, kG, kPre>(fa, flush_smem);
+}
+
+
 
 }  // namespace lps

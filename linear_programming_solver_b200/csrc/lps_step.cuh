@@ -139,6 +139,14 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
   const long long jlo = (long long)cta * W, jhi = (jlo + W < ld) ? jlo + W : ld;
   const int scribe = G - 1;
   unsigned int tag = a.tag0;
+  const unsigned long long t_start = (cta == scribe && tid == 0) ? globaltimer_ns() : 0ull;
+  // the panel's own clock (host: LPS_DEBUG=1 prints it): dbg_ns[14] += duration, dbg_ns[15] += pivots
+  auto clock_out = [&](int pivots_done) {
+    if (cta == scribe && tid == 0) {
+      ctl->dbg_ns[14] += globaltimer_ns() - t_start;
+      ctl->dbg_ns[15] += (unsigned long long)pivots_done;
+    }
+  };
   bool b_lag = false;        // bvec does not include the most recent pivot yet (its r[n] was not known in time)
   int l_last = -1;           // that pivot's leaving row (local, -1: not mine)
   __syncthreads();
@@ -307,7 +315,8 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
         ctl->base.l_cur = (verdict == kPivotCap) ? l : -1;
         ctl->e_nx[par] = e;
       }
-      return;                                           // bvec is up to date: phase A settled it (or e == kNone: nothing pending... see below)
+      clock_out(t);
+      return;                                           // (bvec is rebuilt from the tableau when the next run starts)
     }
     // ---------------- phase B: leaving row, objective row, next entering column ----------------
     const bool i_own = !kSharded || (l >= a.row0 && l < a.row1);
@@ -424,6 +433,7 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
     l_last = lloc;
   }
   settle_b();
+  clock_out(t);
 }
 
 // one block step: panel of the next block on CTAs [0, P), pass of the current block on the rest
@@ -435,6 +445,31 @@ kb_step(const __grid_constant__ StepArgs a, const __grid_constant__ CUtensorMap 
   extern __shared__ __align__(1024) unsigned char step_smem[];
   if ((int)blockIdx.x < a.panel_ctas) panel_role<kSharded, Shape::kThreads>(a, reinterpret_cast<double*>(step_smem));
   else sweep_role<Shape>(a.sw, &tmT0, &tmT1, &tmA, &tmR, step_smem);
+}
+
+// the same step with the cp.async pass (flush_role, lps_blocked.cuh) instead of the TMA pipeline
+template <bool kSharded, int kLanes, int kU, int kG, bool kPre>
+__global__ void __launch_bounds__(kFlushThreads * kLanes, 1)
+kb_step_flush(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(1024) unsigned char step_smem[];
+  if ((int)blockIdx.x < a.panel_ctas) {
+    panel_role<kSharded, kFlushThreads * kLanes>(a, reinterpret_cast<double*>(step_smem));
+  } else {
+    FlushArgs fa;
+    fa.ctl = a.sw.ctl;
+    fa.Tbuf[0] = a.sw.Tbuf[0];
+    fa.Tbuf[1] = a.sw.Tbuf[1];
+    fa.ld = a.sw.ld;
+    fa.mloc = a.mloc;
+    fa.Acols = a.Acols;
+    fa.apitch = a.apitch;
+    fa.Rrows = a.peers.rowbuf[a.rank];
+    fa.block = a.block;
+    fa.q = a.sw.q;
+    fa.inplace = a.sw.inplace;
+    fa.ncta = a.sw.ncta;
+    flush_role<kLanes, kU, kG, kPre>(fa, reinterpret_cast<double*>(step_smem));
+  }
 }
 
 // run set-up of the look-ahead loop: the running b column and objective row start as the tableau's own

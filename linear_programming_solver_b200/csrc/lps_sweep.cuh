@@ -167,6 +167,59 @@ __device__ __forceinline__ void st128_stream(double* p, double x, double y) {
   asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(x), "d"(y) : "memory");
 }
 
+// The rare path of the pass, out of line so that its registers (and its division calls) do not weigh on the
+// allocation of the hot loop: a partial block, or a pending pivot OVERWRITES some of the warp's cells in this
+// sub-pass (its leaving row is one of the thread's rows / its entering column one of the warp's).  A compact
+// rolled loop that takes r_u from the chunk's shared-memory slice instead of the register copy — same values,
+// same operations in the same order.  The thread's cells travel by value (in registers, both ways).
+template <int kR, int kH>
+struct SweepCells {
+  double2 v[kR][kH];
+};
+template <int kR, int kH>
+__device__ __noinline__ SweepCells<kR, kH> sweep_special(SweepCells<kR, kH> x, unsigned int sa /* shared address of a_0[i] */,
+                                                         int a_pitch /* kSR */, const double* srb /* r slice + my column */,
+                                                         int bw, int t, unsigned int smask, int i, int j,
+                                                         unsigned int actbits, const int* s_l, const int* s_e,
+                                                         const double* s_p) {
+  for (int u = 0; u < t; u++) {
+    double av[kR];
+#pragma unroll
+    for (int k = 0; k < kR; k += 2) {
+      const double2 v = lds128(sa + (unsigned int)((u * a_pitch + k) * sizeof(double)));
+      av[k] = v.x;
+      av[k + 1] = v.y;
+    }
+    double rv[2 * kH];
+#pragma unroll
+    for (int h = 0; h < kH; h++) {
+      const double2 v = ((actbits >> h) & 1u) ? *reinterpret_cast<const double2*>(srb + (size_t)u * bw + 64 * h)
+                                              : make_double2(0.0, 0.0);
+      rv[2 * h] = v.x;
+      rv[2 * h + 1] = v.y;
+    }
+    const bool hit = (smask >> u) & 1u;
+    const int lk = hit ? s_l[u] - i : -1;      // its leaving row among my rows (else out of 0..kR-1)
+    const int ce = hit ? s_e[u] - j : -1;      // its entering column among mine: 0, 1 (, 64, 65)
+    const double pu = s_p[u];
+#pragma unroll
+    for (int k = 0; k < kR; k++) {
+#pragma unroll
+      for (int h = 0; h < kH; h++) {
+        if (k == lk) {                         // LPState.java:137-146
+          x.v[k][h].x = rv[2 * h];
+          x.v[k][h].y = rv[2 * h + 1];
+        } else {
+          const double q = (ce == 64 * h || ce == 64 * h + 1) ? -ddiv_call(av[k], pu) : 0.0;   // :157 / :172
+          x.v[k][h].x = (ce == 64 * h) ? q : __dsub_rn(x.v[k][h].x, __dmul_rn(av[k], rv[2 * h]));      // :162-164 / :177
+          x.v[k][h].y = (ce == 64 * h + 1) ? q : __dsub_rn(x.v[k][h].y, __dmul_rn(av[k], rv[2 * h + 1]));
+        }
+      }
+    }
+  }
+  return x;
+}
+
 struct SweepArgs {
   CtlS* ctl;
   double* Tbuf[2];             // the tableau buffers, (mloc+1) x ld each; ctl->cur_at[q] names the current one.
@@ -327,6 +380,9 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
         bool act[kH];
 #pragma unroll
         for (int h = 0; h < kH; h++) act[h] = (jt + 64 * h < bw) && (j + 64 * h < a.ld);
+        unsigned int actbits = 0;
+#pragma unroll
+        for (int h = 0; h < kH; h++) actbits |= act[h] ? (1u << h) : 0u;
         int i = ib + rlane * kR;                         // my first row of the stage's first sub-pass
         double* out = dst + (long long)i * a.ld + j;
         if constexpr (Shape::kPipe) {
@@ -388,36 +444,16 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
                 update(u, av);
               }
             } else {
-              for (int u = 0; u < t; u++) {              // see the rolled loop of the plain consumer below
-                double av[kR];
-                load_a(u, av);
-                double rv[kC];
+              SweepCells<kR, kH> xs;
 #pragma unroll
-                for (int h = 0; h < kH; h++) {
-                  const double2 v = act[h] ? *reinterpret_cast<const double2*>(srb + (size_t)u * bw + jt + 64 * h)
-                                           : make_double2(0.0, 0.0);
-                  rv[2 * h] = v.x;
-                  rv[2 * h + 1] = v.y;
-                }
-                const bool hit = (smask >> u) & 1u;
-                const int lk = hit ? s_l[u] - i : -1;
-                const int ce = hit ? s_e[u] - j : -1;
-                const double pu = s_p[u];
+              for (int k = 0; k < kR; k++)
 #pragma unroll
-                for (int k = 0; k < kR; k++) {
+                for (int h = 0; h < kH; h++) xs.v[k][h] = x[k][h];
+              xs = sweep_special<kR, kH>(xs, sa, kSR, srb + jt, bw, t, smask, i, j, actbits, s_l, s_e, s_p);
 #pragma unroll
-                  for (int h = 0; h < kH; h++) {
-                    if (k == lk) {                       // LPState.java:137-146
-                      x[k][h].x = rv[2 * h];
-                      x[k][h].y = rv[2 * h + 1];
-                    } else {
-                      const double q = (ce == 64 * h || ce == 64 * h + 1) ? -ddiv_call(av[k], pu) : 0.0;   // :157 / :172
-                      x[k][h].x = (ce == 64 * h) ? q : __dsub_rn(x[k][h].x, __dmul_rn(av[k], rv[2 * h]));
-                      x[k][h].y = (ce == 64 * h + 1) ? q : __dsub_rn(x[k][h].y, __dmul_rn(av[k], rv[2 * h + 1]));
-                    }
-                  }
-                }
-              }
+              for (int k = 0; k < kR; k++)
+#pragma unroll
+                for (int h = 0; h < kH; h++) x[k][h] = xs.v[k][h];
               fetch_next();
             }
             __syncwarp();
@@ -493,40 +529,16 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
                 update(u, av);
               }
             } else {
-              // a partial block, or a pending pivot OVERWRITES some of my warp's cells in this sub-pass (its
-              // leaving row is one of my rows / its entering column one of my warp's): rare, so a compact rolled
-              // loop that takes r_u from the chunk's shared-memory slice instead of the register copy — same
-              // values, same operations in the same order
-              for (int u = 0; u < t; u++) {
-                double av[kR];
-                load_a(u, av);
-                double rv[kC];
+              SweepCells<kR, kH> xs;
 #pragma unroll
-                for (int h = 0; h < kH; h++) {
-                  const double2 v = act[h] ? *reinterpret_cast<const double2*>(srb + (size_t)u * bw + jt + 64 * h)
-                                           : make_double2(0.0, 0.0);
-                  rv[2 * h] = v.x;
-                  rv[2 * h + 1] = v.y;
-                }
-                const bool hit = (smask >> u) & 1u;
-                const int lk = hit ? s_l[u] - ip : -1;   // its leaving row among my rows (else out of 0..kR-1)
-                const int ce = hit ? s_e[u] - j : -1;    // its entering column among mine: 0, 1 (, 64, 65)
-                const double pu = s_p[u];
+              for (int k = 0; k < kR; k++)
 #pragma unroll
-                for (int k = 0; k < kR; k++) {
+                for (int h = 0; h < kH; h++) xs.v[k][h] = x[k][h];
+              xs = sweep_special<kR, kH>(xs, sa, kSR, srb + jt, bw, t, smask, ip, j, actbits, s_l, s_e, s_p);
 #pragma unroll
-                  for (int h = 0; h < kH; h++) {
-                    if (k == lk) {                       // LPState.java:137-146
-                      x[k][h].x = rv[2 * h];
-                      x[k][h].y = rv[2 * h + 1];
-                    } else {
-                      const double q = (ce == 64 * h || ce == 64 * h + 1) ? -ddiv_call(av[k], pu) : 0.0;   // :157 / :172
-                      x[k][h].x = (ce == 64 * h) ? q : __dsub_rn(x[k][h].x, __dmul_rn(av[k], rv[2 * h]));  // :162-164 / :177
-                      x[k][h].y = (ce == 64 * h + 1) ? q : __dsub_rn(x[k][h].y, __dmul_rn(av[k], rv[2 * h + 1]));
-                    }
-                  }
-                }
-              }
+              for (int k = 0; k < kR; k++)
+#pragma unroll
+                for (int h = 0; h < kH; h++) x[k][h] = xs.v[k][h];
             }
             if (p == kP - 1) {
               __syncwarp();
