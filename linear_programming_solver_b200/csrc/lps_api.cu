@@ -880,6 +880,11 @@ int launch_step(lps_handle h) {
   h->panel_launches += 1;
   sa.tag0 = h->panel_launches * 64u;
   h->look_launches += 1;
+  {
+    const char* hv = std::getenv("LPS_L2_HINTS");
+    sa.hints = hv ? std::atoi(hv) : 0;
+  }
+  sa.stage_doubles = (int)((step_uses_flush(h) ? step_flush_smem(h, step_flush_kg(h, h->step_grid - P)) : step_smem_bytes(h)) / sizeof(double));
   if (step_uses_flush(h)) {
     const int kg = step_flush_kg(h, h->step_grid - P);
     const size_t smem = step_flush_smem(h, kg);

@@ -47,6 +47,35 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// L2 eviction priorities (createpolicy): the tableau streams through the 126 MB L2 once per pass, the pending
+// columns / rows (a few MB) are re-read by every pivot of the panel, so the stream is marked evict_first and
+// the panel's operands evict_last
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ D4 ld256_hint(const double* p, unsigned long long pol) {
+  D4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st256_hint(double* p, const D4& v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z),
+               "d"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gmem_src, unsigned long long pol) {
+  unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem_src), "l"(pol) : "memory");
+}
 constexpr int kColThreads = 128;
 constexpr int kPanelMax = 20;
 // The panel kernels replay up to kPanelMax pending pivots on a handful of cells per thread.  A
@@ -452,7 +481,7 @@ constexpr unsigned long long kPanelSpinNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 // Arrive-and-wait of the whole co-resident grid, shaped for latency: every CTA's thread 0 fences
 // and takes a ticket; the last arriver re-arms the ticket counter and stores the step's tag into
-// ONE go word that the other CTAs' thread 0 poll (relaxed loads, one acquire fence at the end).
+// ONE go word that the other CTAs' thread 0 poll (relaxed loads, then one acquire fence).
 // Whatever the CTAs wrote before the call (their slots, their share of the pending row / column)
 // is visible to every CTA after it.  False if a peer raised ctl->abort or the wait timed out.
 __device__ __forceinline__ bool panel_sync(CtlS* ctl, unsigned int* counter, unsigned int* go, unsigned int tag) {
@@ -474,9 +503,10 @@ __device__ __forceinline__ bool panel_sync(CtlS* ctl, unsigned int* counter, uns
             (globaltimer_ns() - t0 > kPanelSpinNs || ldcg_s32(&ctl->abort) != 0)) { alive = 0; break; }
       }
     }
-    // no acquire fence here: everything read across CTAs after this point is read with L1-bypassing
-    // loads (ld.global.cg / ld.volatile) that are issued only once the go word has been seen, and the
-    // producers fenced before taking their ticket, so the data is already at the L2 they are served from
+    // acquire side of the hand-off: the relaxed polls above carry no ordering, so one gpu-scope fence once
+    // the go word has been seen orders every later read of this CTA (after the closing bar.sync) behind the
+    // producers' fenced tickets (round 1 relied on L1-bypassing loads alone: a data race under the PTX model)
+    fence_acq_rel_gpu();
     s_alive = alive;
   }
   __syncthreads();
@@ -695,6 +725,7 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
                     (globaltimer_ns() - t0 > kPanelSpinNs || ldcg_s32(&ctl->abort) != 0)) { ok = 0; break; }
               }
             }
+            fence_acq_rel_gpu();      // acquire: pairs with CTA 0's st.release of the go word
             c.slack = ldcg_f64(&a.gwin->slack);
             c.p = ldcg_f64(&a.gwin->p);
             c.row = ldcg_s32(&a.gwin->row);
@@ -892,6 +923,7 @@ struct FlushArgs {
   int q;                   // launch parity = pending set
   int inplace;
   int ncta;
+  int hints;               // bit 0: evict_first on the stream's loads, bit 1: on its stores
 };
 
 template <int kLanes, int kU, int kG, bool kPre>   // kPre: prefetch the lane's next group of rows into L2
@@ -911,6 +943,10 @@ __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
   const double* const Acols = fa.Acols + (size_t)set * fa.block * apitch;
   const double* const Rrows = fa.Rrows + (size_t)set * fa.block * ld;
   __shared__ bool s_last;
+  // out of place = beside a panel (look-ahead loop): mark the stream evict_first so that the panel's operands
+  // survive in L2; the stand-alone in-place pass keeps the plain accesses it was tuned with
+  const bool kStreamL = !fa.inplace && (fa.hints & 1), kStreamS = !fa.inplace && (fa.hints & 2);
+  const unsigned long long pol_stream = l2_evict_first_policy();
   if (t > 0) {
   double* const s_r = smem;                                      // [2][t][kStripCols]
   double* const s_a = smem + (size_t)2 * t * kStripCols;         // [2][t][kCH]
@@ -998,7 +1034,7 @@ __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
       auto load_group = [&](D4 (&x)[kU], int i) {
 #pragma unroll
         for (int k = 0; k < kU; k++)
-          if (i + k < i_end) x[k] = ld256(sbase + (long long)(i + k) * ld);
+          if (i + k < i_end) x[k] = kStreamL ? ld256_hint(sbase + (long long)(i + k) * ld, pol_stream) : ld256(sbase + (long long)(i + k) * ld);
           else x[k].x = x[k].y = x[k].z = x[k].w = 0.0;
       };
       // replay the pending pivots on one group of rows held in registers, then store it
@@ -1080,7 +1116,10 @@ __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
         }
 #pragma unroll
         for (int k = 0; k < kU; k++)
-          if (i + k < i_end) st256(base + (long long)(i + k) * ld, x[k]);
+          if (i + k < i_end) {
+            if (kStreamS) st256_hint(base + (long long)(i + k) * ld, x[k], pol_stream);
+            else st256(base + (long long)(i + k) * ld, x[k]);
+          }
       };
       // the lane's NEXT group of rows (in this chunk, else the first one of the next chunk) is pulled
       // into L2 while this group is replayed: prefetches hold no register and no scoreboard
@@ -1152,6 +1191,7 @@ kb_flush(CtlS* ctl, double* T, long long ld, int mloc, const double* Acols, long
   fa.block = block;
   fa.q = 0;
   fa.inplace = 1;
+  fa.hints = 0;
   fa.ncta = (int)gridDim.x;
   flush_role<kLanes, kU, kG, kPre>(fa, flush_smem);
 }

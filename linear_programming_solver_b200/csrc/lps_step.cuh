@@ -51,6 +51,9 @@ struct StepArgs {
   long long log_cap;
   int* pos2var;
   unsigned int tag0;
+  int hints;                       // L2 eviction hints (env LPS_L2_HINTS, default off: no measurable effect, profiles/r02_summary.md):
+                                   // bit 0 / 1 stream loads / stores evict_first, bit 2 panel operands evict_last
+  int stage_doubles;               // doubles of dynamic shared memory the panel role may use as operand staging
 };
 
 // arrive-and-wait of the `ncta` panel CTAs (see panel_sync in lps_blocked.cuh).  The waiter issues one
@@ -133,12 +136,14 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
     s_rp[tid] = rows_q + (size_t)tid * ld;
   }
   // my share of the rows (objective row included) and of the columns: contiguous ranges
-  const int RW = (mloc + 1 + G - 1) / G;
+  const int RW = ((mloc + 1 + G - 1) / G + 1) & ~1;      // even: a thread takes rows (i, i+1) with 16-byte copies
   const int ilo = cta * RW, ihi = min(ilo + RW, mloc + 1);
   const int W = (int)((((ld + G - 1) / G) + 3) / 4 * 4);
   const long long jlo = (long long)cta * W, jhi = (jlo + W < ld) ? jlo + W : ld;
   const int scribe = G - 1;
   unsigned int tag = a.tag0;
+  const unsigned long long pol_keep = l2_evict_last_policy();   // pending columns / rows: re-read by every pivot
+  const bool keep = (a.hints & 4) != 0;
   const unsigned long long t_start = (cta == scribe && tid == 0) ? globaltimer_ns() : 0ull;
   // the panel's own clock (host: LPS_DEBUG=1 prints it): dbg_ns[14] += duration, dbg_ns[15] += pivots
   auto clock_out = [&](int pivots_done) {
@@ -173,32 +178,60 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
       if (tid < tt) s_re[tid] = ldcg_f64(s_rp[tid] + e);   // r_u[e]: written by other CTAs, behind a sync
       double* const acol = acols_w + (size_t)t * a.apitch;
       const double rn = s_rn;
-      for (int i0 = ilo; i0 < ihi; i0 += NT) {
-        const int i = i0 + tid;
-        double xe = 0.0, bi = 0.0;
-        if (i < ihi) {
-          for (int u = 0; u < tt; u++) cp_async8(s_op + u * NT + tid, s_ap[u] + i);
-          xe = T[(long long)i * ld + e];
-          bi = a.bvec[i];
+      // Two rows per thread and trip, their pending-column entries staged by 16-byte cp.async; a trip takes as many
+      // rows as the staging area holds for tt pending pivots (at most 2 NT).
+      const int cells = min(2 * NT, (a.stage_doubles / max(tt, 1)) & ~1);
+      const int nte = cells / 2;
+      double2* const s_op2 = reinterpret_cast<double2*>(s_op);
+      for (int i0 = ilo; i0 < ihi; i0 += cells) {
+        const int i = i0 + 2 * tid;
+        const bool on = tid < nte && i < ihi;
+        const bool two = on && (i + 1 < ihi);
+        double xe0 = 0.0, xe1 = 0.0, b0 = 0.0, b1 = 0.0;
+        if (on) {
+          if (two) {
+            for (int u = 0; u < tt; u++) { if (keep) cp_async16_hint(s_op2 + u * nte + tid, s_ap[u] + i, pol_keep); else cp_async16(s_op2 + u * nte + tid, s_ap[u] + i); }
+            xe1 = T[(long long)(i + 1) * ld + e];
+            b1 = a.bvec[i + 1];
+          } else {
+            for (int u = 0; u < tt; u++) cp_async8(s_op2 + u * nte + tid, s_ap[u] + i);   // (an 8-byte cp.async with an L2 cache hint raised 'illegal instruction' on B200)
+          }
+          xe0 = T[(long long)i * ld + e];
+          b0 = a.bvec[i];
         }
         cp_async_commit();
         cp_async_wait_all();
         __syncthreads();   // s_re (first trip)
-        if (i < ihi) {
+        if (on) {
           if (b_lag) {     // the previous pivot's update of b, LPState.java:146 / :164
-            const double al = s_op[(tt - 1) * NT + tid];
-            bi = (i == l_last) ? rn : __dsub_rn(bi, __dmul_rn(al, rn));
-            a.bvec[i] = bi;
+            const double2 al = s_op2[(tt - 1) * nte + tid];
+            b0 = (i == l_last) ? rn : __dsub_rn(b0, __dmul_rn(al.x, rn));
+            a.bvec[i] = b0;
+            if (two) {
+              b1 = (i + 1 == l_last) ? rn : __dsub_rn(b1, __dmul_rn(al.y, rn));
+              a.bvec[i + 1] = b1;
+            }
           }
           for (int u = 0; u < tt; u++) {
-            const double au = s_op[u * NT + tid];
-            if (i == s_l[u]) xe = s_re[u];                                     // :137-146
-            else xe = (e == s_e[u]) ? -ddiv_call(au, s_p[u]) : __dsub_rn(xe, __dmul_rn(au, s_re[u]));   // :157 / :162
+            const double2 au = s_op2[u * nte + tid];
+            const double re = s_re[u];
+            const bool ecol = (e == s_e[u]);
+            if (i == s_l[u]) xe0 = re;                                          // :137-146
+            else xe0 = ecol ? -ddiv_call(au.x, s_p[u]) : __dsub_rn(xe0, __dmul_rn(au.x, re));   // :157 / :162
+            if (i + 1 == s_l[u]) xe1 = re;
+            else xe1 = ecol ? -ddiv_call(au.y, s_p[u]) : __dsub_rn(xe1, __dmul_rn(au.y, re));
           }
-          acol[i] = xe;
-          if (i < mloc && !(xe < a.eps)) {                                     // :294-299
-            const double sl = ddiv_call(bi, xe);
-            if (sl < best.slack) { best.slack = sl; best.row = i; best.p = xe; }
+          acol[i] = xe0;
+          if (i < mloc && !(xe0 < a.eps)) {                                     // :294-299
+            const double sl = ddiv_call(b0, xe0);
+            if (sl < best.slack) { best.slack = sl; best.row = i; best.p = xe0; }
+          }
+          if (two) {
+            acol[i + 1] = xe1;
+            if (i + 1 < mloc && !(xe1 < a.eps)) {
+              const double sl = ddiv_call(b1, xe1);
+              if (sl < best.slack) { best.slack = sl; best.row = i + 1; best.p = xe1; }   // strict: the lower row keeps ties
+            }
           }
         }
         __syncthreads();   // s_op is reused by the next trip / phase B
@@ -324,51 +357,70 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
     if (tid < tt) s_al[tid] = i_own ? ldcg_f64(s_ap[tid] + lloc) : 0.0;
     if (tid == NT - 1) s_ce = ldcg_f64(acols_w + (size_t)t * a.apitch + mloc);
     int mine_next = kNone;
-    for (long long jb = jlo; jb < jhi; jb += NT) {
-      const long long j = jb + tid;
-      double cj = 0.0, x = 0.0;
-      if (j < jhi) {
+    {
+    const int cells = min(2 * NT, (a.stage_doubles / max(tt, 1)) & ~1);
+    const int nte = cells / 2;
+    double2* const s_op2 = reinterpret_cast<double2*>(s_op);
+    LLPacket* const ll_mine = reinterpret_cast<LLPacket*>(reinterpret_cast<char*>(a.peers.blk[a.rank]) + a.ll_off) + (size_t)par * ld;
+    for (long long jb = jlo; jb < jhi; jb += cells) {      // column pairs (j, j+1): jlo, jhi and ld are even
+      const long long j = jb + 2 * tid;
+      const bool on = tid < nte && j < jhi;
+      double2 cj = make_double2(0.0, 0.0), x = make_double2(0.0, 0.0);
+      if (on) {
         if (i_own) {
-          for (int u = 0; u < tt; u++) cp_async8(s_op + u * NT + tid, s_rp[u] + j);
-          if (j <= n) x = T[(long long)lloc * ld + j];
+          for (int u = 0; u < tt; u++) { if (keep) cp_async16_hint(s_op2 + u * nte + tid, s_rp[u] + j, pol_keep); else cp_async16(s_op2 + u * nte + tid, s_rp[u] + j); }
+          x = *reinterpret_cast<const double2*>(T + (long long)lloc * ld + j);    // (columns past n hold zeros)
         }
-        if (j < n) cj = a.cvec[j];
+        cj = *reinterpret_cast<const double2*>(a.cvec + j);
       }
       cp_async_commit();
       cp_async_wait_all();
       __syncthreads();     // s_al / s_ce
       bool got = true;
-      if (j < jhi) {
+      if (on) {
         const double ce = s_ce;
-        double r = 0.0;
+        double2 r = make_double2(0.0, 0.0);
         if (i_own) {
           for (int u = 0; u < tt; u++) {
-            const double ru = s_op[u * NT + tid];
+            const double2 ru = s_op2[u * nte + tid];
             if (lloc == s_l[u]) x = ru;                       // the row was pending pivot u's leaving row
-            else x = ((int)j == s_e[u]) ? -ddiv_call(s_al[u], s_p[u]) : __dsub_rn(x, __dmul_rn(s_al[u], ru));
+            else {
+              const double al = s_al[u];
+              x.x = ((int)j == s_e[u]) ? -ddiv_call(al, s_p[u]) : __dsub_rn(x.x, __dmul_rn(al, ru.x));
+              x.y = ((int)j + 1 == s_e[u]) ? -ddiv_call(al, s_p[u]) : __dsub_rn(x.y, __dmul_rn(al, ru.y));
+            }
           }
-          if (j <= n) r = ((int)j == e) ? ddiv_call(1.0, p) : ddiv_call(x, p);      // LPState.java:139-146
-          if (kSharded) {      // compute + broadcast in one kernel: one packet per peer, straight into its memory
+          if (j <= n) r.x = ((int)j == e) ? ddiv_call(1.0, p) : ddiv_call(x.x, p);      // LPState.java:139-146
+          if (j + 1 <= n) r.y = ((int)j + 1 == e) ? ddiv_call(1.0, p) : ddiv_call(x.y, p);
+          if (kSharded) {      // compute + broadcast in one kernel: packets straight into every peer's memory
             for (int k = 0; k < a.world; k++)
-              if (k != a.rank)
-                ll_store(reinterpret_cast<LLPacket*>(reinterpret_cast<char*>(a.peers.blk[k]) + a.ll_off) +
-                             (size_t)par * ld + j, r, seq);
+              if (k != a.rank) {
+                LLPacket* dst = reinterpret_cast<LLPacket*>(reinterpret_cast<char*>(a.peers.blk[k]) + a.ll_off) +
+                                (size_t)par * ld + j;
+                ll_store(dst, r.x, seq);
+                ll_store(dst + 1, r.y, seq);
+              }
           }
         } else {
-          got = ll_load(reinterpret_cast<const LLPacket*>(reinterpret_cast<const char*>(a.peers.blk[a.rank]) + a.ll_off) +
-                            (size_t)par * ld + j, seq, r);
+          got = ll_load(ll_mine + j, seq, r.x) && ll_load(ll_mine + j + 1, seq, r.y);
         }
-        rows_w[(size_t)t * ld + j] = r;                       // this rank's copy of the pending row
+        *reinterpret_cast<double2*>(rows_w + (size_t)t * ld + j) = r;      // this rank's copy of the pending row
+        double2 cn = cj;
         if (j < n) {
-          const double cn = ((int)j == e) ? -ddiv_call(ce, p) : __dsub_rn(cj, __dmul_rn(ce, r));   // :170-178
-          a.cvec[j] = cn;
-          if (cn > a.eps && (int)j < mine_next) mine_next = (int)j;
+          cn.x = ((int)j == e) ? -ddiv_call(ce, p) : __dsub_rn(cj.x, __dmul_rn(ce, r.x));   // :170-178
+          if (cn.x > a.eps && (int)j < mine_next) mine_next = (int)j;
         }
+        if (j + 1 < n) {
+          cn.y = ((int)j + 1 == e) ? -ddiv_call(ce, p) : __dsub_rn(cj.y, __dmul_rn(ce, r.y));
+          if (cn.y > a.eps && (int)j + 1 < mine_next) mine_next = (int)j + 1;
+        }
+        *reinterpret_cast<double2*>(a.cvec + j) = cn;
       }
       if (__syncthreads_or(got ? 0 : 1)) {   // (also: s_op is reused by the next trip / phase A)
         if (tid == 0) { ctl->base.status = kCommTimeout; ctl->abort = 1; __threadfence(); }
         return;
       }
+    }
     }
     mine_next = warp_min_int(mine_next);
     if (lane == 0) s_min[warp] = mine_next;
@@ -468,6 +520,7 @@ kb_step_flush(const __grid_constant__ StepArgs a) {
     fa.q = a.sw.q;
     fa.inplace = a.sw.inplace;
     fa.ncta = a.sw.ncta;
+    fa.hints = a.hints;
     flush_role<kLanes, kU, kG, kPre>(fa, reinterpret_cast<double*>(step_smem));
   }
 }
