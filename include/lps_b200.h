@@ -62,7 +62,8 @@ typedef struct {
                            pivot, 6 = blocked loop with one cooperative panel launch per block followed by
                            the pass, 7 = look-ahead blocked loop: ONE cooperative launch per block runs the
                            pass of block k (out of place, TMA pipeline) and the panel of block k+1 side by
-                           side on disjoint SMs (needs a second tableau buffer; the default above 64 MB) */
+                           side on disjoint SMs (needs a second tableau buffer; the default above 64 MB), 8 = the same
+                           with the pass warps and the panel warps inside every CTA (kb_step_ws) */
   int block_pivots;     /* lps_run: pivots deferred between two passes over the tableau (blocked loop):
                            0 = default (16), 1 = off (every pivot is its own pass), at most 20 (16 for
                            loop_mode 7).  Values are bit-identical for every setting. */

@@ -765,9 +765,24 @@ size_t step_flush_smem(lps_handle h, int kg) {
   return std::max(pass, (size_t)kLookMax * 512 * sizeof(double));
 }
 
+// loop_mode 8: the warp-specialised look-ahead step (kb_step_ws): pass and panel warps in every CTA
+bool step_is_ws(lps_handle h) { return h->opt.loop_mode == 8; }
+int step_ws_kg(lps_handle h) {
+  const long long strips = (h->ld + kStripCols - 1) / kStripCols;
+  const long long per_cta_192 = strips * ((h->m + 192) / 192) / std::max(1, h->sm_count);
+  if (per_cta_192 < 12) return 4;
+  if (per_cta_192 < 40) return 8;
+  return 16;
+}
+size_t step_ws_pass_bytes(lps_handle h, int kg) { return (size_t)h->block * 2 * (kStripCols + 12 * kg) * sizeof(double); }
+size_t step_ws_smem(lps_handle h, int kg) {
+  (void)h; (void)kg;
+  return (size_t)220 * 1024;      // the pass's operand slices, then the panel's staging area takes the rest
+}
+
 bool use_look(lps_handle h) {
   if (!sweep_available(h)) return false;
-  if (h->opt.loop_mode == 7) return true;
+  if (h->opt.loop_mode == 7 || h->opt.loop_mode == 8) return true;
   return h->opt.loop_mode == 0 && shard_bytes(h) > 64e6;
 }
 
@@ -830,7 +845,7 @@ int ensure_look(lps_handle h) {
   }
   int rc = ensure_maps(h, true);
   if (rc) return rc;
-  if (h->step_grid == 0 && step_uses_flush(h)) {
+  if (h->step_grid == 0 && (step_uses_flush(h) || step_is_ws(h))) {
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->dev));
     if (!coop) return fail(h, LPS_ERR_STATE, "device does not support cooperative launch");
@@ -852,8 +867,10 @@ int ensure_look(lps_handle h) {
 int launch_step(lps_handle h) {
   StepArgs sa;
   const int q = (int)(h->look_launches & 1u);
-  const int P = look_panel_ctas(h);
-  fill_sweep_args(h, sa.sw, q, false, P, h->step_grid - P);
+  // the first launch of a run has no pending block to apply: all CTAs take the panel role
+  const bool ws = step_is_ws(h);
+  const int P = (ws || h->look_launches == 0) ? h->step_grid : look_panel_ctas(h);
+  fill_sweep_args(h, sa.sw, q, false, ws ? 0 : P, ws ? h->step_grid : h->step_grid - P);
   sa.mloc = h->m;
   sa.n = h->n;
   sa.row0 = h->row0;
@@ -885,6 +902,18 @@ int launch_step(lps_handle h) {
     sa.hints = hv ? std::atoi(hv) : 0;
   }
   sa.stage_doubles = (int)((step_uses_flush(h) ? step_flush_smem(h, step_flush_kg(h, h->step_grid - P)) : step_smem_bytes(h)) / sizeof(double));
+  if (ws) {
+    const int kg = step_ws_kg(h);
+    const size_t smem = step_ws_smem(h, kg);
+    sa.stage_doubles = (int)((smem - step_ws_pass_bytes(h, kg)) / sizeof(double));
+    const void* wfn;
+    if (h->sharded) wfn = kg == 16 ? (const void*)kb_step_ws<true, 16> : kg == 8 ? (const void*)kb_step_ws<true, 8> : (const void*)kb_step_ws<true, 4>;
+    else wfn = kg == 16 ? (const void*)kb_step_ws<false, 16> : kg == 8 ? (const void*)kb_step_ws<false, 8> : (const void*)kb_step_ws<false, 4>;
+    CK(cudaFuncSetAttribute(wfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* wargs[] = {&sa};
+    CK(cudaLaunchCooperativeKernel(wfn, dim3(h->step_grid), dim3(512), wargs, smem, h->stream));
+    return LPS_OK;
+  }
   if (step_uses_flush(h)) {
     const int kg = step_flush_kg(h, h->step_grid - P);
     const size_t smem = step_flush_smem(h, kg);
@@ -974,10 +1003,12 @@ int run_look(lps_handle h, int64_t max_pivots, lps_run_result* res) {
   if (const char* dbg = std::getenv("LPS_DEBUG")) {
     if (dbg[0] == '1') {
       const unsigned long long* d = h->h_ctls->dbg_ns;
+      const double per = d[15] ? 1e-3 / (double)d[15] : 0.0;
       std::fprintf(stderr, "lps look-ahead run: rank %d  panel role: %.1f us per pivot over %llu pivots (%d CTAs); "
-                           "%lld launches, %lld with a pass\n",
-                   h->rank, d[15] ? 1e-3 * (double)d[14] / (double)d[15] : 0.0, d[15], look_panel_ctas(h), launches,
-                   upd_launches);
+                           "%lld launches, %lld with a pass;  per pivot: column trips %.1f | sync A %.1f | gather+exchange %.1f | "
+                           "row trips %.1f | sync B %.1f | gather+commit %.1f us\n",
+                   h->rank, (double)d[14] * per, d[15], look_panel_ctas(h), launches, upd_launches, (double)d[0] * per,
+                   (double)d[1] * per, (double)d[2] * per, (double)d[3] * per, (double)d[4] * per, (double)d[5] * per);
     }
   }
   // the tableau may have ended up in the second buffer: make it the handle's current one

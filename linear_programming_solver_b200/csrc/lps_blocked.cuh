@@ -903,6 +903,32 @@ __global__ void __launch_bounds__(kPanelThreads, 1) kb_panel(const __grid_consta
 //   s_a [2][t][kCH]   the chunk's slice of the pending columns
 // so the inner loop is LDS + DMUL/DADD only, branch-free for every cell; the few cells a pending
 // pivot overwrites (its leaving row, its entering column) are recomputed afterwards.
+// A subset of a CTA's threads that works as a unit: its own thread numbering and its own hardware barrier.
+// kBarId 0 = the whole CTA (__syncthreads); otherwise threads [kTid0, kTid0 + kCount) meet on named barrier kBarId,
+// so that two groups of one CTA (the pass warps and the panel warps of kb_step_ws) never wait for each other.
+template <int kBarId, int kCount, int kTid0>
+struct CtaGroup {
+  static __device__ __forceinline__ int tid() { return (int)threadIdx.x - kTid0; }
+  static __device__ __forceinline__ void sync() {
+    if (kBarId == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(kBarId), "n"(kCount) : "memory");
+  }
+  static __device__ __forceinline__ int sync_or(int pred) {
+    if (kBarId == 0) return __syncthreads_or(pred);
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %3, 0;\n\t"
+        "barrier.cta.red.or.pred q, %1, %2, p;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "n"(kBarId), "n"(kCount), "r"(pred)
+        : "memory");
+    return r;
+  }
+};
+using WholeCta = CtaGroup<0, 0, 0>;
+
 constexpr int kFlushThreads = 128;
 constexpr int kStripCols = 4 * kFlushThreads;
 
@@ -926,7 +952,7 @@ struct FlushArgs {
   int hints;               // bit 0: evict_first on the stream's loads, bit 1: on its stores
 };
 
-template <int kLanes, int kU, int kG, bool kPre>   // kPre: prefetch the lane's next group of rows into L2
+template <int kLanes, int kU, int kG, bool kPre, class Grp = WholeCta>   // kPre: prefetch the lane's next group of rows into L2
 __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
   constexpr int kThreads = kFlushThreads * kLanes;
   constexpr int kCH = kU * kLanes * kG;            // rows per chunk
@@ -953,7 +979,7 @@ __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
   __shared__ double s_p[kMaxBlock];
   __shared__ int s_l[kMaxBlock], s_e[kMaxBlock];
   __shared__ long long s_claim[2];
-  const int tid = threadIdx.x, lane = tid / kFlushThreads, ltid = tid % kFlushThreads;
+  const int tid = Grp::tid(), lane = tid / kFlushThreads, ltid = tid % kFlushThreads;
   if (tid < t) {
     s_l[tid] = ctl->blk_l2[set][tid];
     s_e[tid] = ctl->blk_e2[set][tid];
@@ -967,7 +993,7 @@ __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
   // further ahead leaves the last CTAs with a private backlog while the others idle, which at a few
   // chunks per CTA (8-way shards, 10,000 x 10,000) was more than half of the kernel
   if (tid == 0) s_claim[0] = (long long)atomicAdd(queue, 1ull);
-  __syncthreads();
+  Grp::sync();
   long long cur = s_claim[0], nxt = 0;
 
   // chunk c's operand slices -> buffer `buf`
@@ -995,7 +1021,7 @@ __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
   while (cur < nchunks) {
     if (tid == 0) s_claim[buf ^ 1] = (long long)atomicAdd(queue, 1ull);   // the chunk after this one
     cp_async_wait_all();
-    __syncthreads();   // this chunk's operands have landed; everyone is done with the other buffer
+    Grp::sync();   // this chunk's operands have landed; everyone is done with the other buffer
     nxt = s_claim[buf ^ 1];
     if (nxt < nchunks) prefetch(nxt, buf ^ 1);
 
@@ -1157,14 +1183,14 @@ __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
   }
   }
   // last pass CTA retires the block
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  Grp::sync();
+  if (Grp::tid() == 0) {
     __threadfence();
     unsigned int tk = atomicAdd(&ctl->blk_ticket, 1u);
     s_last = (tk == (unsigned int)fa.ncta - 1);
   }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  Grp::sync();
+  if (s_last && Grp::tid() == 0) {
     ctl->blk_ticket = 0;
     ctl->blk_queue = 0;
     ctl->blk_pend[set] = 0;

@@ -146,7 +146,7 @@ __global__ void ks_begin_run(CtlS* ctl, long long max_pivots, int reset_next) {
   ctl->cur_at[0] = ctl->cur_at[1] = 0;   // the tableau is in the handle's current buffer when a run starts
   ctl->sweeps_done = 0;
   ctl->blk_fill[0] = ctl->blk_fill[1] = 0;
-  ctl->dbg_ns[14] = ctl->dbg_ns[15] = 0;
+  for (int k = 0; k < 16; k++) ctl->dbg_ns[k] = 0;
   if (reset_next) ctl->e_nx[(ctl->base.npivots + 1) & 1] = kNone;
 }
 

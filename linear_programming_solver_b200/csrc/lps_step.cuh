@@ -59,11 +59,12 @@ struct StepArgs {
 // arrive-and-wait of the `ncta` panel CTAs (see panel_sync in lps_blocked.cuh).  The waiter issues one
 // gpu-scope acquire fence after it has seen the go word: everything the other CTAs wrote before
 // their (fenced) ticket is then visible to every thread of this CTA after the closing bar.sync.
+template <class Grp>
 __device__ __forceinline__ bool step_sync(CtlS* ctl, unsigned int* counter, unsigned int* go, unsigned int tag,
                                           unsigned int ncta) {
   __shared__ int s_alive_step;
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  Grp::sync();
+  if (Grp::tid() == 0) {
     int alive = 1;
     __threadfence();
     const unsigned int old = atomicAdd(counter, 1u);
@@ -82,7 +83,7 @@ __device__ __forceinline__ bool step_sync(CtlS* ctl, unsigned int* counter, unsi
     fence_acq_rel_gpu();
     s_alive_step = alive;
   }
-  __syncthreads();
+  Grp::sync();
   return s_alive_step != 0;
 }
 
@@ -99,7 +100,7 @@ __device__ __forceinline__ void warp_peer_min(PeerCand& c) {
 
 // The panel of one block, run by CTAs [0, a.panel_ctas) with NT threads each.  s_op: dynamic shared
 // memory, kLookMax * NT doubles.
-template <bool kSharded, int NT>
+template <bool kSharded, int NT, class Grp = WholeCta>
 __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
   constexpr int NW = NT / 32;
   CtlS* const ctl = a.sw.ctl;
@@ -112,7 +113,7 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
   __shared__ int s_min[NW], s_min2[NW];
   __shared__ double s_slack, s_pw, s_ce, s_rn;
   __shared__ int s_row, s_ok, s_e2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = Grp::tid(), lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x, G = a.panel_ctas;
   const long long ld = a.sw.ld;
   const int mloc = a.mloc, n = a.n;
@@ -147,14 +148,28 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
   const unsigned long long t_start = (cta == scribe && tid == 0) ? globaltimer_ns() : 0ull;
   // the panel's own clock (host: LPS_DEBUG=1 prints it): dbg_ns[14] += duration, dbg_ns[15] += pivots
   auto clock_out = [&](int pivots_done) {
+    if (cta == scribe && tid == 0 && a.sw.ncta == 0) {
+      // a launch without pass CTAs (the first of a run: nothing is pending yet, so every CTA works on the panel):
+      // the bookkeeping the last pass CTA would do
+      ctl->cur_at[q ^ 1] = ctl->cur_at[q];
+    }
     if (cta == scribe && tid == 0) {
       ctl->dbg_ns[14] += globaltimer_ns() - t_start;
       ctl->dbg_ns[15] += (unsigned long long)pivots_done;
     }
   };
+  unsigned long long t_mark = t_start;
+  // phase clock of the scribe CTA's thread 0: dbg_ns[k] += time since the previous mark (printed with LPS_DEBUG=1)
+  auto mark = [&](int k) {
+    if (cta == scribe && tid == 0) {
+      const unsigned long long now = globaltimer_ns();
+      ctl->dbg_ns[k] += now - t_mark;
+      t_mark = now;
+    }
+  };
   bool b_lag = false;        // bvec does not include the most recent pivot yet (its r[n] was not known in time)
   int l_last = -1;           // that pivot's leaving row (local, -1: not mine)
-  __syncthreads();
+  Grp::sync();
 
   // bring bvec up to date with the most recent pivot (slot tp + t - 1) for my rows
   auto settle_b = [&]() {
@@ -201,7 +216,7 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
         }
         cp_async_commit();
         cp_async_wait_all();
-        __syncthreads();   // s_re (first trip)
+        Grp::sync();   // s_re (first trip)
         if (on) {
           if (b_lag) {     // the previous pivot's update of b, LPState.java:146 / :164
             const double2 al = s_op2[(tt - 1) * nte + tid];
@@ -234,13 +249,14 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
             }
           }
         }
-        __syncthreads();   // s_op is reused by the next trip / phase B
+        Grp::sync();   // s_op is reused by the next trip / phase B
       }
       b_lag = false;
     }
+    mark(0);                                            // phase A trips
     warp_peer_min(best);
     if (lane == 0) s_red[warp] = best;
-    __syncthreads();
+    Grp::sync();
     if (tid == 0) {
       PeerCand c = s_red[0];
       for (int k = 1; k < NW; k++) {
@@ -252,10 +268,11 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
       mine->p = c.p;
       mine->row = c.row;
     }
-    if (!step_sync(ctl, a.syncw + 0, a.syncw + 32, tag, G)) {
+    if (!step_sync<Grp>(ctl, a.syncw + 0, a.syncw + 32, tag, G)) {
       if (tid == 0) { ctl->base.status = kCommTimeout; ctl->abort = 1; __threadfence(); }
       return;
     }
+    mark(1);                                            // sync A
     {
       PeerCand c;
       c.slack = a.inf; c.row = kNone; c.p = 0.0;
@@ -269,7 +286,7 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
       }
       warp_peer_min(c);
       if (lane == 0) s_red2[warp] = c;
-      __syncthreads();
+      Grp::sync();
     }
     if (warp == 0) {
       PeerCand c;
@@ -330,9 +347,10 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
       }
       if (lane == 0) { s_slack = c.slack; s_pw = c.p; s_row = c.row; s_ok = ok; }
     }
-    __syncthreads();
+    Grp::sync();
     const int l = (s_row == kNone) ? -1 : s_row;       // global row (== local on a single GPU)
     const double p = s_pw;
+    mark(2);                                            // gather of the partials + cross-rank candidate exchange
     if (kSharded && !s_ok) {
       if (tid == 0) { ctl->base.status = kCommTimeout; ctl->abort = 1; __threadfence(); }
       return;
@@ -375,7 +393,7 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
       }
       cp_async_commit();
       cp_async_wait_all();
-      __syncthreads();     // s_al / s_ce
+      Grp::sync();     // s_al / s_ce
       bool got = true;
       if (on) {
         const double ce = s_ce;
@@ -416,12 +434,13 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
         }
         *reinterpret_cast<double2*>(a.cvec + j) = cn;
       }
-      if (__syncthreads_or(got ? 0 : 1)) {   // (also: s_op is reused by the next trip / phase A)
+      if (Grp::sync_or(got ? 0 : 1)) {   // (also: s_op is reused by the next trip / phase A)
         if (tid == 0) { ctl->base.status = kCommTimeout; ctl->abort = 1; __threadfence(); }
         return;
       }
     }
     }
+    mark(3);                                            // phase B trips (row replay / packets, objective row)
     mine_next = warp_min_int(mine_next);
     if (lane == 0) s_min[warp] = mine_next;
     if (tid == 0) {          // every CTA keeps its own copy of the pending pivots' scalars
@@ -431,16 +450,17 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
       s_ap[tt] = acols_w + (size_t)t * a.apitch;
       s_rp[tt] = rows_w + (size_t)t * ld;
     }
-    __syncthreads();
+    Grp::sync();
     if (tid == 0) {
       int v = s_min[0];
       for (int k = 1; k < NW; k++) v = min(v, s_min[k]);
       a.mins[cta * kMinStride] = (unsigned long long)(unsigned int)v;
     }
-    if (!step_sync(ctl, a.syncw + 64, a.syncw + 96, tag, G)) {
+    if (!step_sync<Grp>(ctl, a.syncw + 64, a.syncw + 96, tag, G)) {
       if (tid == 0) { ctl->base.status = kCommTimeout; ctl->abort = 1; __threadfence(); }
       return;
     }
+    mark(4);                                            // sync B
     {
       int v = kNone;
       for (int k = tid; k < G; k += NT) {
@@ -451,13 +471,13 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
       v = warp_min_int(v);
       if (lane == 0) s_min2[warp] = v;
       if (tid == NT - 1) s_rn = ldcg_f64(rows_w + (size_t)t * ld + n);     // b_l / p of this pivot: the next b update
-      __syncthreads();
+      Grp::sync();
       if (tid == 0) {
         int m2 = s_min2[0];
         for (int k = 1; k < NW; k++) m2 = min(m2, s_min2[k]);
         s_e2 = m2;
       }
-      __syncthreads();
+      Grp::sync();
     }
     const int e2 = s_e2;
     if (cta == scribe && tid == 0) {                       // commit pivot(e, l)
@@ -483,6 +503,7 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
     tag += 1;
     b_lag = true;
     l_last = lloc;
+    mark(5);                                            // gather of the minima + commit
   }
   settle_b();
   clock_out(t);
@@ -522,6 +543,40 @@ kb_step_flush(const __grid_constant__ StepArgs a) {
     fa.ncta = a.sw.ncta;
     fa.hints = a.hints;
     flush_role<kLanes, kU, kG, kPre>(fa, reinterpret_cast<double*>(step_smem));
+  }
+}
+
+// The look-ahead step with BOTH roles in every CTA: warps 0-11 run the cp.async pass (three row-group lanes),
+// warps 12-15 the panel.  The panel is a latency chain — its threads mostly wait for L2 / DRAM / a grid-wide
+// decision / an NVLink packet — so instead of lending it whole SMs that then sit idle (kb_step_flush), every SM
+// lends it four warps whose waiting costs nothing, and the panel runs at full-GPU width: one or two trips per
+// step instead of a dozen.  The two groups have their own named barriers and never wait for each other.
+template <bool kSharded, int kG>
+__global__ void __launch_bounds__(512, 1)
+kb_step_ws(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(1024) unsigned char step_smem[];
+  constexpr int kPassThreads = 384, kPanelThreads2 = 128;
+  constexpr int kCH = 4 * 3 * kG;
+  const size_t pass_bytes = (size_t)a.block * 2 * (kStripCols + kCH) * sizeof(double);
+  if ((int)threadIdx.x < kPassThreads) {
+    FlushArgs fa;
+    fa.ctl = a.sw.ctl;
+    fa.Tbuf[0] = a.sw.Tbuf[0];
+    fa.Tbuf[1] = a.sw.Tbuf[1];
+    fa.ld = a.sw.ld;
+    fa.mloc = a.mloc;
+    fa.Acols = a.Acols;
+    fa.apitch = a.apitch;
+    fa.Rrows = a.peers.rowbuf[a.rank];
+    fa.block = a.block;
+    fa.q = a.sw.q;
+    fa.inplace = a.sw.inplace;
+    fa.ncta = (int)gridDim.x;
+    fa.hints = a.hints;
+    flush_role<3, 4, kG, true, CtaGroup<1, kPassThreads, 0>>(fa, reinterpret_cast<double*>(step_smem));
+  } else {
+    panel_role<kSharded, kPanelThreads2, CtaGroup<2, kPanelThreads2, kPassThreads>>(
+        a, reinterpret_cast<double*>(step_smem + pass_bytes));
   }
 }
 

@@ -2,7 +2,8 @@
 pass over the tableau.  loop_mode=5 runs the panel as two launches per pivot (kb_col, kb_row),
 loop_mode=6 as one cooperative launch per block (kb_panel) followed by the pass, loop_mode=7 is the
 look-ahead loop: one cooperative launch per block runs the TMA pass of block k (out of place) and the
-panel of block k+1 side by side (kb_step).  Every value must still be
+panel of block k+1 side by side on disjoint SMs (kb_step_flush / kb_step), loop_mode=8 the same with pass warps and
+panel warps inside every CTA (kb_step_ws).  Every value must still be
 bit-identical to the pivot-per-pass kernels and to the binary64 oracle — pivot sequence, verdict,
 every cell.  `-m gpu`."""
 import threading
@@ -15,7 +16,7 @@ from oracle import tier_f
 pytestmark = pytest.mark.gpu
 
 VERDICT = {tier_f.OPTIMAL: 1, tier_f.UNBOUNDED: 2, tier_f.PIVOT_CAP: 3}
-MODES = [5, 6, 7]
+MODES = [5, 6, 7, 8]
 
 
 def _L():
@@ -260,7 +261,7 @@ def test_blocked_multi_gpu(world, mode):
         assert np.array_equal(s.c, ref.c) and s.v == ref.v[0]
 
 
-@pytest.mark.parametrize("mode", [6, 7])
+@pytest.mark.parametrize("mode", [6, 7, 8])
 @pytest.mark.parametrize("ctas,chunk", [(1, 12), (3, 24), (40, 0), (147, 48)])
 def test_look_ahead_role_split_and_chunking(mode, ctas, chunk):
     """the result may not depend on how many CTAs run the panel, nor on the chunk height of the pass"""
@@ -275,7 +276,7 @@ def test_look_ahead_role_split_and_chunking(mode, ctas, chunk):
     _same_state(st, ref)
 
 
-@pytest.mark.parametrize("mode", [6, 7])
+@pytest.mark.parametrize("mode", [6, 7, 8])
 def test_look_ahead_repeated_runs_and_buffer_swaps(mode):
     """many short runs: the tableau ends up in either buffer of the out-of-place pass, partial blocks,
     caps at every position of a block"""
@@ -300,7 +301,7 @@ def test_look_ahead_repeated_runs_and_buffer_swaps(mode):
     _same_state(st, ref)
 
 
-@pytest.mark.parametrize("mode", [6, 7])
+@pytest.mark.parametrize("mode", [6, 7, 8])
 def test_handle_reloaded_with_a_larger_lp(mode):
     """one handle, a small LP and then a large one: the pass kernel chosen for the second size must get
     its shared-memory opt-in too"""

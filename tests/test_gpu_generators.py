@@ -36,7 +36,7 @@ def test_generators_match_their_restatements(m, n):
         assert st.v == 0.0
 
 
-@pytest.mark.parametrize("mode", [1, 6, 7])
+@pytest.mark.parametrize("mode", [1, 6, 7, 8])
 @pytest.mark.parametrize("col", ["first", "last"])
 def test_unbounded_family(col, mode):
     from linear_programming_solver_b200 import _native as N
@@ -58,7 +58,7 @@ def test_unbounded_family(col, mode):
         L.LPSolver().solve(L.LPStandardForm(A, b, c, m, n, True))
 
 
-@pytest.mark.parametrize("mode", [1, 2, 6, 7])
+@pytest.mark.parametrize("mode", [1, 2, 6, 7, 8])
 def test_assignment_family_is_exact_and_matches_the_decimal_oracle(mode):
     """degenerate, totally unimodular: entries stay in {-1,0,1}; pivot sequence identical to the
     reference's 15-digit decimal arithmetic (Tier D) as well as to the binary64 twin"""

@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--blocks", default="4,8,16,24,32")
     ap.add_argument("--variants", default="0")
     ap.add_argument("--mode", type=int, default=6, help="5 = two launches per pivot, 6 = one cooperative panel launch "
-                    "per block + the pass, 7 = look-ahead loop (panel and pass side by side)")
+                    "per block + the pass, 7 = look-ahead loop (panel and pass side by side), 8 = look-ahead, both roles in every CTA")
     ap.add_argument("--panel", default="0", help="look-ahead loop: CTAs of the panel role (comma list, 0 = auto)")
     ap.add_argument("--chunk", default="0", help="TMA pass: rows per chunk (comma list, 0 = auto)")
     a = ap.parse_args()
