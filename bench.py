@@ -447,7 +447,8 @@ def run_ours(args):
     value = pivots / (dev_ms / 1e3)
     peak, peak_src = measured_peak()
     per_launch = round(pivots / max(upd_n, 1))
-    kernels = ("lps::k_update", "lps::kb_step (pass role: sweep_role)" if args.loop_mode in (0, 7) else "lps::kb_flush / kb_sweep")
+    loop_desc = st.loop_description()
+    kernels = ("lps::k_update", loop_desc.split(": ", 1)[-1])
     rl = roofline_block(bytes_pp, pivots, upd_ms, upd_n, kernels, peak, peak_src,
                         traffic=ncu_traffic("kb_step_n1" if per_launch > 1 else "k_update_n1"), fp64_peak=fp64_peak,
                         cells=(m + 1) * (n + 1))
@@ -458,7 +459,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_block(m, n, args.seed),
-        "details": {"pivots_per_step": P, "loop": loop_name(rl, args.loop_mode),
+        "details": {"pivots_per_step": P, "loop": loop_desc,
                     "l2": "tableau (6.4 GB) is far larger than the 126 MB L2; no flush needed",
                     "timing": "CUDA events on the library's stream around each step; the pass kernel's launches are "
                               "bracketed by their own events on the same stream",

@@ -195,6 +195,8 @@ int lps_algorithmic_bytes_per_pivot(lps_handle h, int64_t *bytes); /* 16*(m+1)*(
    in FP64 thread-instructions per second, timed with CUDA events on the handle's stream for about `ms`
    milliseconds.  This is the FP64 roof the pass is held against beside the HBM one. */
 int lps_measure_fp64_issue_rate(lps_handle h, double ms, double *inst_per_s);
+/* Which loop shape lps_run uses for the loaded LP (bench / log records): kernel names, SM split, pivots per pass. */
+int lps_loop_description(lps_handle h, char *buf, int cap);
 
 #ifdef __cplusplus
 }

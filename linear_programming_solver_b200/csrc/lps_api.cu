@@ -98,6 +98,9 @@ struct lps_handle_s {
   int step_grid = 0;                      // cooperative grid of kb_step (0 = not sized yet)
   int sweep_grid = 0;                     // grid of the stand-alone kb_sweep (0 = not sized yet)
   unsigned int look_launches = 0;         // launch counter of the look-ahead loop: parity + tag source
+  int tuned_P = 0;                        // panel CTAs chosen by tune_split() for a tableau of tuned_m x tuned_ld
+  int tuned_m = 0;
+  long long tuned_ld = 0;
 
   std::vector<cudaEvent_t> ev;  // time_kernels event pool
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -710,7 +713,7 @@ int sweep_chunk_rows(lps_handle h, int ncta) {
     const long long bw = std::min<long long>(pass_cols(h), h->ld);
     const long long nstrips = (h->ld + bw - 1) / bw;
     cr = (int)(((long long)(h->m + 1) * nstrips) / (24ll * std::max(1, ncta)));
-    cr = std::min(cr, 240);
+    cr = std::min(cr, 120);   // taller chunks let the CTAs drift apart: 120 beat 240 by 5 % on the 20,000-row LP
   }
   const int sr = pass_stage_rows(h);
   cr = std::max(sr, (cr / sr) * sr);
@@ -757,9 +760,16 @@ int step_flush_kg(lps_handle h, int ncta) {
   if (per_cta_256 < 40) return 8;
   return 16;
 }
-// the look-ahead loop's pass role: the cp.async kernel by default (the faster one on B200 so far,
-// profiles/r02_pass_shapes.md); update_variant >= 10 selects a shape of the TMA pipeline
-bool step_uses_flush(lps_handle h) { return h->opt.update_variant <= 9; }
+// the look-ahead loop's pass role (update_variant 0..9: the cp.async kernel, >= 10: a shape of the TMA pipeline)
+bool step_uses_flush(lps_handle h) {
+  if (h->opt.update_variant >= 10) return false;
+  if (h->opt.update_variant >= 0) return true;
+  // default: the TMA pipeline (shape D) on multi-GB shards — there the GPU runs against its power cap for seconds
+  // and the TMA pass, with half the shared-memory operand traffic, keeps the higher clock (5.6 - 6.0 k pivots/s
+  // against 5.3 - 5.4 k on the 20,000 x 40,000 LP, sustained); the cp.async pass on smaller shards, where it is
+  // 10 - 15 % faster per step (profiles/r02_summary.md)
+  return shard_bytes(h) < 2.5e9;
+}
 size_t step_flush_smem(lps_handle h, int kg) {
   const size_t pass = (size_t)h->block * 2 * (kStripCols + 4 * 4 * kg) * sizeof(double);
   return std::max(pass, (size_t)kLookMax * 512 * sizeof(double));
@@ -788,26 +798,61 @@ bool use_look(lps_handle h) {
 
 int look_panel_ctas(lps_handle h) {
   int P = h->opt.panel_ctas;
+  if (P <= 0 && h->tuned_P > 0 && h->tuned_m == h->m && h->tuned_ld == h->ld) P = h->tuned_P;     // tune_split()
   if (P <= 0) {
-    // Both roles are throughput-bound on the SMs they get: the pass needs ~0.37 ms per GB of shard on the whole
-    // GPU (16 pivots replayed, FP64 / issue-bound), a panel pivot ~6.5 us per trip of its CTAs over the local rows
-    // and (on the owner of the leaving row) over the columns, plus ~10 us of syncs and exchange (measured,
-    // profiles/r02_summary.md).  Pick the split that minimises the slower of the two.
-    const double pass_ms_full = 0.37 * shard_bytes(h) / 1e9 * h->block / 16.0 + 0.02;
-    const long long rows = (h->sharded ? h->m_total / h->world : h->m) + 1;
-    const int nt = step_uses_flush(h) ? 512 : pass_threads(h);
+    // Both roles are throughput-bound on the SMs they get (measured on B200, profiles/r02_summary.md):
+    //   pass   ~0.37 ms per GB of shard on the whole GPU (16 pivots replayed) + 0.1 ms of tail on small shards,
+    //          proportionally slower on fewer SMs;
+    //   panel  ~10 us of syncs per pivot + 11.5 us per 1000 cells (local rows + columns) that one of its CTAs has
+    //          to replay; sharded (two NVLink hops): ~19 us + 10.3 us per 1000 cells (14.9 with one cell per thread, 8 ranks).
+    // Pick the split that minimises the slower of the two.
+    const double pass_ms_full = (0.367 * shard_bytes(h) / 1e9 + 0.11) * h->block / 16.0;
+    const double rows = (double)((h->sharded ? h->m_total / h->world : h->m) + 1);
     double best = 1e30;
     P = 8;
     for (int p = 2; p <= h->sm_count / 2; p++) {
-      const double trips = (double)((rows + (long long)nt * p - 1) / ((long long)nt * p)) +
-                           (double)((h->ld + (long long)nt * p - 1) / ((long long)nt * p));
-      const double panel_ms = h->block * (6.5 * trips + 10.0) * 1e-3;
+      const double kcells = 1e-3 * (rows + (double)h->ld) / p;
+      const double panel_ms = h->block * (h->world >= 8 ? 19.0 + 14.9 * kcells : h->world > 1 ? 19.0 + 10.3 * kcells
+                                                                                                : 10.0 + 11.5 * kcells) * 1e-3;
       const double pass_ms = pass_ms_full * h->sm_count / (double)(h->sm_count - p);
       const double step = std::max(panel_ms, pass_ms);
       if (step < best) { best = step; P = p; }
     }
   }
   return std::max(1, std::min(P, h->sm_count - 1));
+}
+
+// After a run: re-fit the panel / pass split from the two roles' own clocks (CtlS::dbg_ns, written by the panel's
+// scribe and by the last pass CTA to retire).  The model above only has to be right enough for the first run of a
+// handle; every later run starts from what the previous one measured on this GPU, at this shard size, with these
+// peers.  panel(p) = block * (A + B / p) with the sync share A fixed and B from the measurement; pass(p) = the
+// measured pass scaled by the CTAs it had.  The pivots do not depend on the split (tests: panel_ctas sweep).
+void tune_split(lps_handle h) {
+  if (h->opt.panel_ctas > 0 || step_is_ws(h)) return;
+  if (const char* tv = std::getenv("LPS_SPLIT_TUNE")) if (tv[0] == '0') return;
+  const unsigned long long* d = h->h_ctls->dbg_ns;
+  if (d[15] < (unsigned long long)(2 * h->block) || d[11] < 2) return;
+  const int G = h->step_grid, P0 = look_panel_ctas(h);
+  if (P0 < 1 || P0 >= G) return;
+  const double tp = (double)d[14] / (double)d[15] * 1e-3;               // panel: us per pivot on P0 CTAs
+  const double pass0 = (double)d[10] / (double)d[11] * 1e-3;            // pass: us per block on G - P0 CTAs
+  const double A = std::min(h->world > 1 ? 19.0 : 10.0, 0.6 * tp);
+  const double B = (tp - A) * P0;
+  const double full = pass0 * (G - P0) / G;
+  auto cost = [&](int p) { return std::max(h->block * (A + B / p), full * G / (double)(G - p)); };
+  const int reach = std::max(2, P0 / 3);
+  int best = P0;
+  for (int p = std::max(2, P0 - reach); p <= std::min(G / 2, P0 + reach); p++)
+    if (cost(p) < cost(best)) best = p;
+  if (cost(best) < 0.98 * cost(P0)) {
+    h->tuned_P = best;
+    h->tuned_m = h->m;
+    h->tuned_ld = h->ld;
+  } else if (h->tuned_P <= 0) {
+    h->tuned_P = P0;
+    h->tuned_m = h->m;
+    h->tuned_ld = h->ld;
+  }
 }
 
 // second tableau buffer, running vectors, sync words, tensor maps, kernel attributes
@@ -897,6 +942,12 @@ int launch_step(lps_handle h) {
   h->panel_launches += 1;
   sa.tag0 = h->panel_launches * 64u;
   h->look_launches += 1;
+  {
+    // 3: a row / column pair per thread, trips pipelined without CTA barriers (lps_step.cuh); 2 and 1: the
+    // barrier-per-trip forms with two cells / one cell per thread (kept for comparison, profiles/r02_summary.md)
+    const char* cv = std::getenv("LPS_PANEL_CELLS");
+    sa.cells = cv ? std::max(1, std::min(3, std::atoi(cv))) : 3;
+  }
   {
     const char* hv = std::getenv("LPS_L2_HINTS");
     sa.hints = hv ? std::atoi(hv) : 0;
@@ -1006,11 +1057,14 @@ int run_look(lps_handle h, int64_t max_pivots, lps_run_result* res) {
       const double per = d[15] ? 1e-3 / (double)d[15] : 0.0;
       std::fprintf(stderr, "lps look-ahead run: rank %d  panel role: %.1f us per pivot over %llu pivots (%d CTAs); "
                            "%lld launches, %lld with a pass;  per pivot: column trips %.1f | sync A %.1f | gather+exchange %.1f | "
-                           "row trips %.1f | sync B %.1f | gather+commit %.1f us\n",
+                           "row trips %.1f | sync B %.1f | gather+commit %.1f us;  pass role: %.1f us per block;  "
+                           "first launch (all CTAs on the panel): %.1f us per pivot\n",
                    h->rank, (double)d[14] * per, d[15], look_panel_ctas(h), launches, upd_launches, (double)d[0] * per,
-                   (double)d[1] * per, (double)d[2] * per, (double)d[3] * per, (double)d[4] * per, (double)d[5] * per);
+                   (double)d[1] * per, (double)d[2] * per, (double)d[3] * per, (double)d[4] * per, (double)d[5] * per,
+                   d[11] ? (double)d[10] * 1e-3 / (double)d[11] : 0.0, d[13] ? (double)d[12] * 1e-3 / (double)d[13] : 0.0);
     }
   }
+  tune_split(h);
   // the tableau may have ended up in the second buffer: make it the handle's current one
   if (h->h_ctls->cur_at[h->look_launches & 1u] == 1) {
     std::swap(h->T, h->T2);
@@ -1778,6 +1832,34 @@ int lps_measure_fp64_issue_rate(lps_handle h, double ms, double* inst_per_s) {
   float el = 0.f;
   CK(cudaEventElapsedTime(&el, h->ev_begin, h->ev_end));
   *inst_per_s = el > 0.f ? per_launch * reps / (el * 1e-3) : 0.0;
+  return LPS_OK;
+}
+
+int lps_loop_description(lps_handle h, char* buf, int cap) {
+  if (!h || !buf || cap <= 0) return LPS_ERR_INVALID;
+  if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");
+  char tmp[512];
+  if (use_look(h)) {
+    const int P = look_panel_ctas(h);
+    if (step_is_ws(h))
+      std::snprintf(tmp, sizeof tmp, "look-ahead blocked loop, %d pivots per pass: lps::kb_step_ws (12 pass warps + 4 panel warps in each of %d CTAs)",
+                    h->block, h->sm_count);
+    else if (step_uses_flush(h))
+      std::snprintf(tmp, sizeof tmp, "look-ahead blocked loop, %d pivots per pass: lps::kb_step_flush (panel role on %d CTAs, cp.async pass role on %d)",
+                    h->block, P, h->sm_count - P);
+    else
+      std::snprintf(tmp, sizeof tmp, "look-ahead blocked loop, %d pivots per pass: lps::kb_step (panel role on %d CTAs, TMA + mbarrier pass role on %d, %d-row stages)",
+                    h->block, P, h->sm_count - P, pass_stage_rows(h));
+  } else if (use_blocked(h)) {
+    std::snprintf(tmp, sizeof tmp, "serial blocked loop, %d pivots per pass: lps::%s then lps::%s", h->block,
+                  h->opt.loop_mode == 5 ? "kb_col + kb_row per pivot" : "kb_panel",
+                  (h->opt.update_variant >= 10 && sweep_available(h)) ? "kb_sweep (TMA)" : "kb_flush (cp.async)");
+  } else if (use_persistent(h)) {
+    std::snprintf(tmp, sizeof tmp, "one pass per pivot, persistent cooperative loop: lps::k_loop");
+  } else {
+    std::snprintf(tmp, sizeof tmp, "one pass per pivot: lps::%s", h->sharded ? "ks_ratio, ks_scale_row, ks_update" : "k_ratio, k_scale_row, k_update");
+  }
+  std::snprintf(buf, (size_t)cap, "%s", tmp);
   return LPS_OK;
 }
 

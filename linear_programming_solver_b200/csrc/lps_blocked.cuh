@@ -46,6 +46,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int kN>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
 
 // L2 eviction priorities (createpolicy): the tableau streams through the 126 MB L2 once per pass, the pending
 // columns / rows (a few MB) are re-read by every pivot of the panel, so the stream is marked evict_first and
@@ -969,6 +971,8 @@ __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
   const double* const Acols = fa.Acols + (size_t)set * fa.block * apitch;
   const double* const Rrows = fa.Rrows + (size_t)set * fa.block * ld;
   __shared__ bool s_last;
+  __shared__ unsigned long long s_t0;
+  if (Grp::tid() == 0) s_t0 = globaltimer_ns();
   // out of place = beside a panel (look-ahead loop): mark the stream evict_first so that the panel's operands
   // survive in L2; the stand-alone in-place pass keeps the plain accesses it was tuned with
   const bool kStreamL = !fa.inplace && (fa.hints & 1), kStreamS = !fa.inplace && (fa.hints & 2);
@@ -1195,7 +1199,11 @@ __device__ __forceinline__ void flush_role(const FlushArgs& fa, double* smem) {
     ctl->blk_queue = 0;
     ctl->blk_pend[set] = 0;
     ctl->cur_at[fa.q ^ 1] = (!fa.inplace && t > 0) ? (cur ^ 1) : cur;   // read by the NEXT launch only
-    if (t > 0) ctl->sweeps_done += 1;
+    if (t > 0) {
+      ctl->sweeps_done += 1;
+      ctl->dbg_ns[10] += globaltimer_ns() - s_t0;      // the pass's own clock: the last CTA to retire (host: split tuning)
+      ctl->dbg_ns[11] += 1;
+    }
     __threadfence();
   }
 }

@@ -251,6 +251,8 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
   const CUtensorMap* const tmT = cur ? tmT1 : tmT0;
   double* const dst = a.Tbuf[a.inplace ? cur : (cur ^ 1)];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned long long s_t0;
+  if (tid == 0) s_t0 = globaltimer_ns();
   double* const tiles = reinterpret_cast<double*>(smem + SM::kOffTiles);
   double* const s_a = reinterpret_cast<double*>(smem + SM::kOffA);
   double* const s_r = reinterpret_cast<double*>(smem + SM::kOffR);
@@ -577,7 +579,11 @@ __device__ __forceinline__ void sweep_role(const SweepArgs& a, const CUtensorMap
     ctl->blk_pend[set] = 0;
     // nobody in THIS launch reads cur_at[q ^ 1]: the next launch does
     ctl->cur_at[a.q ^ 1] = (!a.inplace && t > 0) ? (cur ^ 1) : cur;
-    if (t > 0) ctl->sweeps_done += 1;
+    if (t > 0) {
+      ctl->sweeps_done += 1;
+      ctl->dbg_ns[10] += globaltimer_ns() - s_t0;      // the pass's own clock: the last CTA to retire (host: split tuning)
+      ctl->dbg_ns[11] += 1;
+    }
     __threadfence();
   }
 }

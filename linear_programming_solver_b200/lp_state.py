@@ -260,6 +260,12 @@ class LPState:
         self._ck(self._lib.lps_measure_fp64_issue_rate(self._h, float(ms), byref(x)), "measure_fp64_issue_rate")
         return x.value
 
+    def loop_description(self) -> str:
+        """which kernels lps_run uses for this LP (loop shape, pass kernel, SM split)"""
+        buf = ctypes.create_string_buffer(512)
+        self._ck(self._lib.lps_loop_description(self._h, buf, 512), "loop_description")
+        return buf.value.decode()
+
     def algorithmic_bytes_per_pivot(self) -> int:
         x = c_int64()
         self._ck(self._lib.lps_algorithmic_bytes_per_pivot(self._h, byref(x)), "bytes")

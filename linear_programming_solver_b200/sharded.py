@@ -149,6 +149,7 @@ def bench_sharded(args, dist, rank, world, local_rank, B):
     st = ShardedLPState(m, n, rank, world, synthetic_seed=args.seed, device=local_rank, time_kernels=True, **kw)
     st.attach_via(dist)
     bytes_pp_local = st.algorithmic_bytes_per_pivot()        # this rank's rows (+ objective replica)
+    loop_desc = st.loop_description()
     bytes_pp_global = 16 * (m + 1) * (n + 1)
     mloc = st.row1 - st.row0
 
@@ -232,8 +233,7 @@ def bench_sharded(args, dist, rank, world, local_rank, B):
         peak, peak_src = B.measured_peak()
         value = pivots / (dev_ms_max / 1e3)
         per_launch = round(pivots / max(upd_n, 1))
-        kernels = ("lps::ks_update (per rank)",
-                   "lps::kb_step (per rank; pass role: sweep_role)" if args.loop_mode in (0, 7) else "lps::kb_flush / kb_sweep (per rank)")
+        kernels = ("lps::ks_update (per rank)", loop_desc.split(": ", 1)[-1] + " (per rank)")
         rl = B.roofline_block(bytes_pp_local, pivots, upd_avg_ms * max(upd_n, 1), upd_n, kernels, peak, peak_src,
                               traffic=B.ncu_traffic("kb_step_n%d" % world if per_launch > 1 else "ks_update_n%d" % world),
                               fp64_peak=float(tf[0]), cells=(mloc + 1) * (n + 1))
@@ -242,7 +242,7 @@ def bench_sharded(args, dist, rank, world, local_rank, B):
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": B.config_block(m, n, args.seed),
-            "details": {"pivots_per_step": P, "loop": B.loop_name(rl, args.loop_mode),
+            "details": {"pivots_per_step": P, "loop": loop_desc,
                         "sharding": "rows [k*m/G,(k+1)*m/G) per rank, objective row replicated",
                         "exchange": "ratio candidates + scaled pivot row pushed into peer memory over NVLink "
                                     "inside the kernels (no NCCL in the loop)",

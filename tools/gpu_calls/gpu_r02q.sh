@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2, call Q (8 GPUs): one vs two cells per panel thread on 8 / 4 ranks, defaults otherwise
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+export LPS_DEBUG=1
+timeout 300 python -m pytest tests/test_gpu_blocked.py tests/test_gpu_sharded.py -m gpu -q -k "multi_gpu or sharded or shard or world or gpus" > gpurun_out/r02q_multi.log 2>&1
+echo "multi rc=$?" >> gpurun_out/r02q_multi.log
+run() {
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) \
+    bench.py --gpus $2 --steps 20 --warmup 5 --no-e2e $3 > gpurun_out/r02q_bench_$1.json 2> gpurun_out/r02q_bench_$1.err
+  echo "rc=$?" >> gpurun_out/r02q_bench_$1.err
+}
+run n8 8 ""
+LPS_PANEL_CELLS=2 run n8_c2 8 ""
+run n8_P44 8 "--panel-ctas 44"
+run n4 4 ""
+LPS_PANEL_CELLS=2 run n4_c2 4 ""
+run n2 2 ""
+tail -n 3 gpurun_out/r02q_multi.log; for f in gpurun_out/r02q_bench_*.json; do echo $f; cut -c1-200 $f; done
