@@ -943,10 +943,12 @@ int launch_step(lps_handle h) {
   sa.tag0 = h->panel_launches * 64u;
   h->look_launches += 1;
   {
-    // 3: a row / column pair per thread, trips pipelined without CTA barriers (lps_step.cuh); 2 and 1: the
-    // barrier-per-trip forms with two cells / one cell per thread (kept for comparison, profiles/r02_summary.md)
+    // two rows / columns per panel thread and trip (16-byte staging slots: fewer trips — 135 -> 87 us per pivot at 8
+    // CTAs on one GPU, 58 -> 49 us on 4 ranks); one (8-byte slots) on 8 ranks, where the shorter trips let the
+    // owner's first packets leave earlier (43 -> 40 us).  Forms that did not pay (profiles/r02_summary.md): trips
+    // pipelined without CTA barriers, operands staged by cp.async.bulk, pending rows pinned in L2.
     const char* cv = std::getenv("LPS_PANEL_CELLS");
-    sa.cells = cv ? std::max(1, std::min(3, std::atoi(cv))) : 3;
+    sa.cells = cv ? std::max(1, std::min(2, std::atoi(cv))) : (h->world >= 8 ? 1 : 2);
   }
   {
     const char* hv = std::getenv("LPS_L2_HINTS");

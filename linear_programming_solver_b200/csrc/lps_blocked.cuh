@@ -46,8 +46,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-template <int kN>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
 
 // L2 eviction priorities (createpolicy): the tableau streams through the 126 MB L2 once per pass, the pending
 // columns / rows (a few MB) are re-read by every pivot of the panel, so the stream is marked evict_first and

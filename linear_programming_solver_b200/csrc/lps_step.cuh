@@ -29,7 +29,6 @@
 namespace lps {
 
 constexpr int kLookMax = 2 * kPanelMax;       // previous block + own block
-constexpr int kPanelPipe = 3;                      // sub-trips of the panel's operand staging in flight per thread
 
 struct StepArgs {
   SweepArgs sw;                    // the pass (sw.ctl, sw.Tbuf, sw.ld, sw.q are shared with the panel)
@@ -53,8 +52,8 @@ struct StepArgs {
   int* pos2var;
   unsigned int tag0;
   int hints;                       // L2 eviction hints (env LPS_L2_HINTS, default off: no measurable effect, profiles/r02_summary.md):
-                                   // bit 0 / 1 stream loads / stores evict_first, bit 2 panel operands evict_last
-  int cells;                       // rows / columns per panel thread and trip: 2 (16-byte staging) or 1; 3: pairs, pipelined trips
+                                   // bit 0 / 1: the pass's stream loads / stores evict_first
+  int cells;                       // rows / columns per panel thread and trip: 2 (16-byte staging slots) or 1 (8-byte slots)
   int stage_doubles;               // doubles of dynamic shared memory the panel role may use as operand staging
 };
 
@@ -145,8 +144,6 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
   const long long jlo = (long long)cta * W, jhi = (jlo + W < ld) ? jlo + W : ld;
   const int scribe = G - 1;
   unsigned int tag = a.tag0;
-  const unsigned long long pol_keep = l2_evict_last_policy();   // pending columns / rows: re-read by every pivot
-  const bool keep = (a.hints & 4) != 0;
   const unsigned long long t_start = (cta == scribe && tid == 0) ? globaltimer_ns() : 0ull;
   __shared__ unsigned long long s_dbg[8];
   if (tid < 8) s_dbg[tid] = 0;
@@ -205,82 +202,14 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
       // rows as the staging area holds for tt pending pivots (at most 2 NT).
       // (a.cells == 1: one row per thread — shorter trips, so that on a sharded solve the owner's first packets
       // leave earlier and the peers' work overlaps the owner's later trips)
-      if (a.cells >= 3) {
-        // Pipelined trips (a.cells == 3).  A thread only ever reads the staging slots it filled itself, so the trips
-        // need no CTA barrier; kPanelPipe sub-trips are in flight per thread (cp.async groups), each carrying a row
-        // pair's tt pending-column entries, its two entries of column e and its two b entries.  The panel's loads
-        // compete with the pass for the memory system (loaded latency: microseconds): the old trips paid that
-        // latency once per trip, these pay it once per phase.
-        const int rowsb = tt + 2;
-        const int nte = max(1, min(NT, (a.stage_doubles / 2) / (kPanelPipe * rowsb)));
-        const int span = 2 * nte;
-        const int ntr = (ihi - ilo + span - 1) / span;
-        double2* const ring = reinterpret_cast<double2*>(s_op);
-        auto issue = [&](int k) {
-          const int i = ilo + k * span + 2 * tid;
-          if (k < ntr && tid < nte && i < ihi) {
-            double2* const sb = ring + (size_t)(k % kPanelPipe) * rowsb * nte + tid;
-            if (i + 1 < ihi) {
-              for (int u = 0; u < tt; u++) cp_async16(sb + u * nte, s_ap[u] + i);
-              cp_async8(&sb[tt * nte].y, T + (long long)(i + 1) * ld + e);
-              cp_async16(sb + (tt + 1) * nte, a.bvec + i);
-            } else {
-              for (int u = 0; u < tt; u++) cp_async8(sb + u * nte, s_ap[u] + i);
-              cp_async8(sb + (tt + 1) * nte, a.bvec + i);
-            }
-            cp_async8(&sb[tt * nte].x, T + (long long)i * ld + e);
-          }
-          cp_async_commit();
-        };
-        for (int k = 0; k < kPanelPipe - 1; k++) issue(k);
-        Grp::sync();   // s_re
-        for (int k = 0; k < ntr; k++) {
-          issue(k + kPanelPipe - 1);
-          cp_async_wait_group<kPanelPipe - 1>();
-          const int i = ilo + k * span + 2 * tid;
-          if (tid < nte && i < ihi) {
-            const double2* const sb = ring + (size_t)(k % kPanelPipe) * rowsb * nte + tid;
-            const bool two = i + 1 < ihi;
-            const double2 xe = sb[tt * nte], bb = sb[(tt + 1) * nte];
-            double xe0 = xe.x, xe1 = xe.y, b0 = bb.x, b1 = bb.y;     // (.y: unused garbage on an odd tail)
-            if (b_lag) {     // the previous pivot's update of b, LPState.java:146 / :164
-              const double2 al = sb[(tt - 1) * nte];
-              b0 = (i == l_last) ? rn : __dsub_rn(b0, __dmul_rn(al.x, rn));
-              a.bvec[i] = b0;
-              if (two) {
-                b1 = (i + 1 == l_last) ? rn : __dsub_rn(b1, __dmul_rn(al.y, rn));
-                a.bvec[i + 1] = b1;
-              }
-            }
-            for (int u = 0; u < tt; u++) {
-              const double2 au = sb[u * nte];
-              const double re = s_re[u];
-              const bool ecol = (e == s_e[u]);
-              if (i == s_l[u]) xe0 = re;                                          // :137-146
-              else xe0 = ecol ? -ddiv_call(au.x, s_p[u]) : __dsub_rn(xe0, __dmul_rn(au.x, re));   // :157 / :162
-              if (i + 1 == s_l[u]) xe1 = re;
-              else xe1 = ecol ? -ddiv_call(au.y, s_p[u]) : __dsub_rn(xe1, __dmul_rn(au.y, re));
-            }
-            acol[i] = xe0;
-            if (i < mloc && !(xe0 < a.eps)) {                                     // :294-299
-              const double sl = ddiv_call(b0, xe0);
-              if (sl < best.slack) { best.slack = sl; best.row = i; best.p = xe0; }
-            }
-            if (two) {
-              acol[i + 1] = xe1;
-              if (i + 1 < mloc && !(xe1 < a.eps)) {
-                const double sl = ddiv_call(b1, xe1);
-                if (sl < best.slack) { best.slack = sl; best.row = i + 1; best.p = xe1; }   // strict: the lower row keeps ties
-              }
-            }
-          }
-        }
-        cp_async_wait_all();
-      } else {
+      {
       const int cpt = a.cells;
-      const int nte = min(NT, (a.stage_doubles / 2) / max(tt, 1));      // threads per trip: one 16-byte slot each per pending pivot
+      const int nte = min(NT, (a.stage_doubles / cpt) / max(tt, 1));    // threads per trip: one slot of cpt doubles each per pending pivot
       const int cells = cpt * nte;
-      double2* const s_op2 = reinterpret_cast<double2*>(s_op);
+      double* const slot0 = s_op + tid * cpt;
+      const int sstride = nte * cpt;
+      auto slot = [&](int u) { return slot0 + u * sstride; };
+      auto slot2 = [&](int u) { const double* q = slot(u); return cpt == 2 ? *reinterpret_cast<const double2*>(q) : make_double2(*q, 0.0); };
       for (int i0 = ilo; i0 < ihi; i0 += cells) {
         const int i = i0 + cpt * tid;
         const bool on = tid < nte && i < ihi;
@@ -288,11 +217,11 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
         double xe0 = 0.0, xe1 = 0.0, b0 = 0.0, b1 = 0.0;
         if (on) {
           if (two) {
-            for (int u = 0; u < tt; u++) { if (keep) cp_async16_hint(s_op2 + u * nte + tid, s_ap[u] + i, pol_keep); else cp_async16(s_op2 + u * nte + tid, s_ap[u] + i); }
+            for (int u = 0; u < tt; u++) cp_async16(slot(u), s_ap[u] + i);
             xe1 = T[(long long)(i + 1) * ld + e];
             b1 = a.bvec[i + 1];
           } else {
-            for (int u = 0; u < tt; u++) cp_async8(s_op2 + u * nte + tid, s_ap[u] + i);   // (an 8-byte cp.async with an L2 cache hint raised 'illegal instruction' on B200)
+            for (int u = 0; u < tt; u++) cp_async8(slot(u), s_ap[u] + i);   // (an 8-byte cp.async with an L2 cache hint raised 'illegal instruction' on B200)
           }
           xe0 = T[(long long)i * ld + e];
           b0 = a.bvec[i];
@@ -302,7 +231,7 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
         Grp::sync();   // s_re (first trip)
         if (on) {
           if (b_lag) {     // the previous pivot's update of b, LPState.java:146 / :164
-            const double2 al = s_op2[(tt - 1) * nte + tid];
+            const double2 al = slot2(tt - 1);
             b0 = (i == l_last) ? rn : __dsub_rn(b0, __dmul_rn(al.x, rn));
             a.bvec[i] = b0;
             if (two) {
@@ -311,7 +240,7 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
             }
           }
           for (int u = 0; u < tt; u++) {
-            const double2 au = s_op2[u * nte + tid];
+            const double2 au = slot2(u);
             const double re = s_re[u];
             const bool ecol = (e == s_e[u]);
             if (i == s_l[u]) xe0 = re;                                          // :137-146
@@ -459,88 +388,14 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
     if (tid < tt) s_al[tid] = i_own ? ldcg_f64(s_ap[tid] + lloc) : 0.0;
     if (tid == NT - 1) s_ce = ldcg_f64(acols_w + (size_t)t * a.apitch + mloc);
     int mine_next = kNone;
-    if (a.cells >= 3) {
-      // pipelined trips, as in phase A: a column pair's tt pending-row entries, its two entries of row l and its
-      // two objective entries per sub-trip (a rank that does not own row l stages the objective entries only)
-      const int rowsb = tt + 2;
-      const int nte = max(1, min(NT, (a.stage_doubles / 2) / (kPanelPipe * rowsb)));
-      const long long span = 2 * nte;
-      const int ntr = (int)((jhi - jlo + span - 1) / span);
-      double2* const ring = reinterpret_cast<double2*>(s_op);
-      LLPacket* const ll_mine = reinterpret_cast<LLPacket*>(reinterpret_cast<char*>(a.peers.blk[a.rank]) + a.ll_off) + (size_t)par * ld;
-      auto issue = [&](int k) {
-        const long long j = jlo + k * span + 2 * tid;      // (jlo, jhi and ld are even: always a full pair)
-        if (k < ntr && tid < nte && j < jhi) {
-          double2* const sb = ring + (size_t)(k % kPanelPipe) * rowsb * nte + tid;
-          if (i_own) {
-            for (int u = 0; u < tt; u++) cp_async16(sb + u * nte, s_rp[u] + j);
-            cp_async16(sb + tt * nte, T + (long long)lloc * ld + j);               // (columns past n hold zeros)
-          }
-          cp_async16(sb + (tt + 1) * nte, a.cvec + j);
-        }
-        cp_async_commit();
-      };
-      for (int k = 0; k < kPanelPipe - 1; k++) issue(k);
-      Grp::sync();     // s_al / s_ce
-      const double ce = s_ce;
-      bool got = true;
-      for (int k = 0; k < ntr && got; k++) {
-        issue(k + kPanelPipe - 1);
-        cp_async_wait_group<kPanelPipe - 1>();
-        const long long j = jlo + k * span + 2 * tid;
-        if (tid < nte && j < jhi) {
-          const double2* const sb = ring + (size_t)(k % kPanelPipe) * rowsb * nte + tid;
-          const double2 cj = sb[(tt + 1) * nte];
-          double2 r = make_double2(0.0, 0.0);
-          if (i_own) {
-            double2 x = sb[tt * nte];
-            for (int u = 0; u < tt; u++) {
-              const double2 ru = sb[u * nte];
-              if (lloc == s_l[u]) x = ru;                       // the row was pending pivot u's leaving row
-              else {
-                const double al = s_al[u];
-                x.x = ((int)j == s_e[u]) ? -ddiv_call(al, s_p[u]) : __dsub_rn(x.x, __dmul_rn(al, ru.x));
-                x.y = ((int)j + 1 == s_e[u]) ? -ddiv_call(al, s_p[u]) : __dsub_rn(x.y, __dmul_rn(al, ru.y));
-              }
-            }
-            if (j <= n) r.x = ((int)j == e) ? ddiv_call(1.0, p) : ddiv_call(x.x, p);      // LPState.java:139-146
-            if (j + 1 <= n) r.y = ((int)j + 1 == e) ? ddiv_call(1.0, p) : ddiv_call(x.y, p);
-            if (kSharded) {      // compute + broadcast in one kernel: packets straight into every peer's memory
-              for (int k2 = 0; k2 < a.world; k2++)
-                if (k2 != a.rank) {
-                  LLPacket* dst = reinterpret_cast<LLPacket*>(reinterpret_cast<char*>(a.peers.blk[k2]) + a.ll_off) +
-                                  (size_t)par * ld + j;
-                  ll_store(dst, r.x, seq);
-                  ll_store(dst + 1, r.y, seq);
-                }
-            }
-          } else {
-            got = ll_load(ll_mine + j, seq, r.x);
-            got = ll_load(ll_mine + j + 1, seq, r.y) && got;
-          }
-          double2 cn = cj;
-          if (j < n) {
-            cn.x = ((int)j == e) ? -ddiv_call(ce, p) : __dsub_rn(cj.x, __dmul_rn(ce, r.x));   // :170-178
-            if (cn.x > a.eps && (int)j < mine_next) mine_next = (int)j;
-          }
-          if (j + 1 < n) {
-            cn.y = ((int)j + 1 == e) ? -ddiv_call(ce, p) : __dsub_rn(cj.y, __dmul_rn(ce, r.y));
-            if (cn.y > a.eps && (int)j + 1 < mine_next) mine_next = (int)j + 1;
-          }
-          *reinterpret_cast<double2*>(rows_w + (size_t)t * ld + j) = r;      // this rank's copy of the pending row
-          *reinterpret_cast<double2*>(a.cvec + j) = cn;
-        }
-      }
-      cp_async_wait_all();
-      if (Grp::sync_or(got ? 0 : 1)) {   // (also: the ring is reused by the next pivot with another slot layout)
-        if (tid == 0) { ctl->base.status = kCommTimeout; ctl->abort = 1; __threadfence(); }
-        return;
-      }
-    } else {
+    {
     const int cpt = a.cells;
-    const int nte = min(NT, (a.stage_doubles / 2) / max(tt, 1));
+    const int nte = min(NT, (a.stage_doubles / cpt) / max(tt, 1));
     const int cells = cpt * nte;
-    double2* const s_op2 = reinterpret_cast<double2*>(s_op);
+    double* const slot0 = s_op + tid * cpt;
+      const int sstride = nte * cpt;
+      auto slot = [&](int u) { return slot0 + u * sstride; };
+    auto slot2 = [&](int u) { const double* q = slot(u); return cpt == 2 ? *reinterpret_cast<const double2*>(q) : make_double2(*q, 0.0); };
     LLPacket* const ll_mine = reinterpret_cast<LLPacket*>(reinterpret_cast<char*>(a.peers.blk[a.rank]) + a.ll_off) + (size_t)par * ld;
     for (long long jb = jlo; jb < jhi; jb += cells) {      // columns j (and j+1: jlo, jhi and ld are even)
       const long long j = jb + cpt * tid;
@@ -550,10 +405,10 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
       if (on) {
         if (i_own) {
           if (two) {
-            for (int u = 0; u < tt; u++) { if (keep) cp_async16_hint(s_op2 + u * nte + tid, s_rp[u] + j, pol_keep); else cp_async16(s_op2 + u * nte + tid, s_rp[u] + j); }
+            for (int u = 0; u < tt; u++) cp_async16(slot(u), s_rp[u] + j);
             x = *reinterpret_cast<const double2*>(T + (long long)lloc * ld + j);    // (columns past n hold zeros)
           } else {
-            for (int u = 0; u < tt; u++) cp_async8(s_op2 + u * nte + tid, s_rp[u] + j);
+            for (int u = 0; u < tt; u++) cp_async8(slot(u), s_rp[u] + j);
             x.x = T[(long long)lloc * ld + j];
           }
         }
@@ -569,7 +424,7 @@ __device__ __forceinline__ void panel_role(const StepArgs& a, double* s_op) {
         double2 r = make_double2(0.0, 0.0);
         if (i_own) {
           for (int u = 0; u < tt; u++) {
-            const double2 ru = s_op2[u * nte + tid];
+            const double2 ru = slot2(u);
             if (lloc == s_l[u]) x = ru;                       // the row was pending pivot u's leaving row
             else {
               const double al = s_al[u];
