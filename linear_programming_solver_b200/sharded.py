@@ -149,7 +149,6 @@ def bench_sharded(args, dist, rank, world, local_rank, B):
     st = ShardedLPState(m, n, rank, world, synthetic_seed=args.seed, device=local_rank, time_kernels=True, **kw)
     st.attach_via(dist)
     bytes_pp_local = st.algorithmic_bytes_per_pivot()        # this rank's rows (+ objective replica)
-    loop_desc = st.loop_description()
     bytes_pp_global = 16 * (m + 1) * (n + 1)
     mloc = st.row1 - st.row0
 
@@ -228,6 +227,7 @@ def bench_sharded(args, dist, rank, world, local_rank, B):
                "d2h_bytes_per_step": int(8 * (m + world * (n + 1)) + 4 * world * (m + n)),
                "pivots_per_call": Pe, "seconds_per_call": best,
                "what": "per rank: shard load from pinned host memory + IPC attach + run(%d) + read b,c,v,positions" % Pe}
+    loop_desc = st.loop_description()       # after the timed region: the split the runs settled on
     bad = False
     if rank == 0:
         peak, peak_src = B.measured_peak()
