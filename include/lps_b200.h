@@ -197,6 +197,16 @@ int lps_algorithmic_bytes_per_pivot(lps_handle h, int64_t *bytes); /* 16*(m+1)*(
 int lps_measure_fp64_issue_rate(lps_handle h, double ms, double *inst_per_s);
 /* Which loop shape lps_run uses for the loaded LP (bench / log records): kernel names, SM split, pivots per pass. */
 int lps_loop_description(lps_handle h, char *buf, int cap);
+/* The SM split of the look-ahead step (loop_mode 7), as pure host arithmetic (no device, no handle; no reference
+   analogue): how many of `grid` CTAs decide the next block's pivots while the others apply the current block.
+   lps_plan_split_model: the a-priori choice for a shard of rows_local x pitch doubles on `world` ranks -- what the
+   first run of a handle uses.  lps_plan_split_tuned: the choice after a run that measured the panel role at
+   panel_us_per_pivot on `current` CTAs and the pass role at pass_us_per_block on the others -- what every later
+   run uses (options.panel_ctas > 0 overrides both).  Both return the CTA count (>= 1), or LPS_ERR_INVALID.
+   The split changes timing only: pivots and results are identical for every value. */
+int lps_plan_split_model(int grid, int block_pivots, int world, int64_t rows_local, int64_t pitch);
+int lps_plan_split_tuned(int grid, int block_pivots, int world, int current, double panel_us_per_pivot,
+                         double pass_us_per_block);
 
 #ifdef __cplusplus
 }

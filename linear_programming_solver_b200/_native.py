@@ -84,6 +84,8 @@ SIGNATURES = {
     "lps_algorithmic_bytes_per_pivot": (c_int, [c_void_p, POINTER(c_int64)]),
     "lps_measure_fp64_issue_rate": (c_int, [c_void_p, c_double, _dp]),
     "lps_loop_description": (c_int, [c_void_p, c_char_p, c_int]),
+    "lps_plan_split_model": (c_int, [c_int, c_int, c_int, c_int64, c_int64]),
+    "lps_plan_split_tuned": (c_int, [c_int, c_int, c_int, c_int, c_double, c_double]),
     "lps_shard_generate_dense": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_uint64, c_int]),
     "lps_shard_generate_lp": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint64, c_int]),
     "lps_shard_load": (c_int, [c_void_p, c_int, c_int, c_int, c_int, _dp, c_int64, _dp, _dp, c_double]),

@@ -796,63 +796,66 @@ bool use_look(lps_handle h) {
   return h->opt.loop_mode == 0 && shard_bytes(h) > 64e6;
 }
 
+// The a-priori split of the look-ahead step (lps_plan_split_model in the C ABI; no device involved).  Both roles
+// are throughput-bound on the SMs they get (measured on B200, profiles/r02_summary.md):
+//   pass   ~0.37 ms per GB of shard on the whole GPU (16 pivots replayed) + 0.1 ms of tail on small shards,
+//          proportionally slower on fewer SMs;
+//   panel  ~10 us of syncs per pivot + 11.5 us per 1000 cells (local rows + columns) that one of its CTAs has
+//          to replay; sharded (two NVLink hops): ~19 us + 10.3 us per 1000 cells (14.9 with one cell per thread, 8 ranks).
+// Pick the split that minimises the slower of the two.  It only seeds the first run of a handle (tune_split).
+int split_model(int grid, int block, int world, long long rows_local, long long ld) {
+  const double shard = 8.0 * (double)(rows_local + 1) * (double)ld;
+  const double pass_ms_full = (0.367 * shard / 1e9 + 0.11) * block / 16.0;
+  double best = 1e30;
+  int P = std::min(8, std::max(1, grid - 1));
+  for (int p = 2; p <= grid / 2; p++) {
+    const double kcells = 1e-3 * ((double)(rows_local + 1) + (double)ld) / p;
+    const double panel_ms = block * (world >= 8 ? 19.0 + 14.9 * kcells : world > 1 ? 19.0 + 10.3 * kcells
+                                                                                    : 10.0 + 11.5 * kcells) * 1e-3;
+    const double pass_ms = pass_ms_full * grid / (double)(grid - p);
+    const double step = std::max(panel_ms, pass_ms);
+    if (step < best) { best = step; P = p; }
+  }
+  return std::max(1, std::min(P, grid - 1));
+}
+
+// The re-fit after a run (lps_plan_split_tuned in the C ABI): panel(p) = block * (A + B / p) with the sync share A
+// fixed and B from the measured panel clock at `cur` CTAs; pass(p) = the measured pass scaled by the CTAs it had.
+// Moves at most a third of the way per run and only for a predicted gain above 2 %.
+int split_tuned(int grid, int block, int world, int cur, double panel_us_per_pivot, double pass_us_per_block) {
+  if (cur < 1 || cur >= grid || !(panel_us_per_pivot > 0.0) || !(pass_us_per_block > 0.0)) return cur;
+  const double A = std::min(world > 1 ? 19.0 : 10.0, 0.6 * panel_us_per_pivot);
+  const double B = (panel_us_per_pivot - A) * cur;
+  const double full = pass_us_per_block * (grid - cur) / grid;
+  auto cost = [&](int p) { return std::max(block * (A + B / p), full * grid / (double)(grid - p)); };
+  const int reach = std::max(2, cur / 3);
+  int best = cur;
+  for (int p = std::max(2, cur - reach); p <= std::min(grid / 2, cur + reach); p++)
+    if (cost(p) < cost(best)) best = p;
+  return cost(best) < 0.98 * cost(cur) ? best : cur;
+}
+
 int look_panel_ctas(lps_handle h) {
   int P = h->opt.panel_ctas;
   if (P <= 0 && h->tuned_P > 0 && h->tuned_m == h->m && h->tuned_ld == h->ld) P = h->tuned_P;     // tune_split()
-  if (P <= 0) {
-    // Both roles are throughput-bound on the SMs they get (measured on B200, profiles/r02_summary.md):
-    //   pass   ~0.37 ms per GB of shard on the whole GPU (16 pivots replayed) + 0.1 ms of tail on small shards,
-    //          proportionally slower on fewer SMs;
-    //   panel  ~10 us of syncs per pivot + 11.5 us per 1000 cells (local rows + columns) that one of its CTAs has
-    //          to replay; sharded (two NVLink hops): ~19 us + 10.3 us per 1000 cells (14.9 with one cell per thread, 8 ranks).
-    // Pick the split that minimises the slower of the two.
-    const double pass_ms_full = (0.367 * shard_bytes(h) / 1e9 + 0.11) * h->block / 16.0;
-    const double rows = (double)((h->sharded ? h->m_total / h->world : h->m) + 1);
-    double best = 1e30;
-    P = 8;
-    for (int p = 2; p <= h->sm_count / 2; p++) {
-      const double kcells = 1e-3 * (rows + (double)h->ld) / p;
-      const double panel_ms = h->block * (h->world >= 8 ? 19.0 + 14.9 * kcells : h->world > 1 ? 19.0 + 10.3 * kcells
-                                                                                                : 10.0 + 11.5 * kcells) * 1e-3;
-      const double pass_ms = pass_ms_full * h->sm_count / (double)(h->sm_count - p);
-      const double step = std::max(panel_ms, pass_ms);
-      if (step < best) { best = step; P = p; }
-    }
-  }
+  if (P <= 0) P = split_model(h->sm_count, h->block, h->world, h->sharded ? h->m_total / h->world : h->m, h->ld);
   return std::max(1, std::min(P, h->sm_count - 1));
 }
 
 // After a run: re-fit the panel / pass split from the two roles' own clocks (CtlS::dbg_ns, written by the panel's
-// scribe and by the last pass CTA to retire).  The model above only has to be right enough for the first run of a
+// scribe and by the last pass CTA to retire).  The model only has to be right enough for the first run of a
 // handle; every later run starts from what the previous one measured on this GPU, at this shard size, with these
-// peers.  panel(p) = block * (A + B / p) with the sync share A fixed and B from the measurement; pass(p) = the
-// measured pass scaled by the CTAs it had.  The pivots do not depend on the split (tests: panel_ctas sweep).
+// peers.  The pivots do not depend on the split (tests: panel_ctas sweep).
 void tune_split(lps_handle h) {
   if (h->opt.panel_ctas > 0 || step_is_ws(h)) return;
   if (const char* tv = std::getenv("LPS_SPLIT_TUNE")) if (tv[0] == '0') return;
   const unsigned long long* d = h->h_ctls->dbg_ns;
   if (d[15] < (unsigned long long)(2 * h->block) || d[11] < 2) return;
-  const int G = h->step_grid, P0 = look_panel_ctas(h);
-  if (P0 < 1 || P0 >= G) return;
-  const double tp = (double)d[14] / (double)d[15] * 1e-3;               // panel: us per pivot on P0 CTAs
-  const double pass0 = (double)d[10] / (double)d[11] * 1e-3;            // pass: us per block on G - P0 CTAs
-  const double A = std::min(h->world > 1 ? 19.0 : 10.0, 0.6 * tp);
-  const double B = (tp - A) * P0;
-  const double full = pass0 * (G - P0) / G;
-  auto cost = [&](int p) { return std::max(h->block * (A + B / p), full * G / (double)(G - p)); };
-  const int reach = std::max(2, P0 / 3);
-  int best = P0;
-  for (int p = std::max(2, P0 - reach); p <= std::min(G / 2, P0 + reach); p++)
-    if (cost(p) < cost(best)) best = p;
-  if (cost(best) < 0.98 * cost(P0)) {
-    h->tuned_P = best;
-    h->tuned_m = h->m;
-    h->tuned_ld = h->ld;
-  } else if (h->tuned_P <= 0) {
-    h->tuned_P = P0;
-    h->tuned_m = h->m;
-    h->tuned_ld = h->ld;
-  }
+  const int P0 = look_panel_ctas(h);
+  h->tuned_P = split_tuned(h->step_grid, h->block, h->world, P0, (double)d[14] / (double)d[15] * 1e-3,
+                           (double)d[10] / (double)d[11] * 1e-3);
+  h->tuned_m = h->m;
+  h->tuned_ld = h->ld;
 }
 
 // second tableau buffer, running vectors, sync words, tensor maps, kernel attributes
@@ -1837,6 +1840,15 @@ int lps_measure_fp64_issue_rate(lps_handle h, double ms, double* inst_per_s) {
   return LPS_OK;
 }
 
+int lps_plan_split_model(int grid, int block_pivots, int world, int64_t rows_local, int64_t pitch) {
+  if (grid < 2 || block_pivots < 1 || world < 1 || rows_local < 0 || pitch < 1) return LPS_ERR_INVALID;
+  return split_model(grid, block_pivots, world, rows_local, pitch);
+}
+int lps_plan_split_tuned(int grid, int block_pivots, int world, int current, double panel_us_per_pivot,
+                         double pass_us_per_block) {
+  if (grid < 2 || block_pivots < 1 || world < 1) return LPS_ERR_INVALID;
+  return split_tuned(grid, block_pivots, world, current, panel_us_per_pivot, pass_us_per_block);
+}
 int lps_loop_description(lps_handle h, char* buf, int cap) {
   if (!h || !buf || cap <= 0) return LPS_ERR_INVALID;
   if (!h->loaded) return fail(h, LPS_ERR_STATE, "nothing loaded");

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call A: parity of the TMA pass + look-ahead loop, then a first timing sweep (one B200)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/r02a_gpu.txt 2>&1
 timeout 900 python -m pytest tests/test_gpu_blocked.py -m gpu -x -q > gpurun_out/r02a_blocked.log 2>&1

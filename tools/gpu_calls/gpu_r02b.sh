@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call B: ncu --set full of the TMA pass (in place, mode 6) and of the fused look-ahead step (mode 7)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 CMD6="python tools/tune_blocked.py 20000 40000 3 --blocks 16 --mode 6 --variants 10"
 CMD7="python tools/tune_blocked.py 20000 40000 3 --blocks 16 --mode 7 --variants 10 --panel 8"

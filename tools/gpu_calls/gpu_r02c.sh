@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call C: 4-columns-per-thread pass shapes, digests of the bench workload, first full bench line
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_blocked.py -m gpu -x -q > gpurun_out/r02c_blocked.log 2>&1
 echo "blocked rc=$?" >> gpurun_out/r02c_blocked.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call D: restructured pass pipeline (chunk descriptors, hinted waits, rolled special path)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_blocked.py -m gpu -x -q > gpurun_out/r02d_blocked.log 2>&1
 echo "blocked rc=$?" >> gpurun_out/r02d_blocked.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call E: pass shapes R8 (8 rows per thread) and F12 (folded producer, 12 consumer warps)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_blocked.py -m gpu -x -q > gpurun_out/r02e_blocked.log 2>&1
 echo "blocked rc=$?" >> gpurun_out/r02e_blocked.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call F: generalized pass shapes A (12 warps R2 P2), B (15 warps, 192-col strips), C (T8), D (T8 P2), E (T8 R6)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_blocked.py -m gpu -x -q > gpurun_out/r02f_blocked.log 2>&1
 echo "blocked rc=$?" >> gpurun_out/r02f_blocked.log

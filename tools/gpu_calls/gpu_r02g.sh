@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call G: software-pipelined consumer (variant 14) vs shapes C (12) / D (13) and kb_flush (0)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_blocked.py -m gpu -x -q > gpurun_out/r02g_blocked.log 2>&1
 echo "blocked rc=$?" >> gpurun_out/r02g_blocked.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call H (2 GPUs): multi-GPU parity tests incl. the look-ahead loop, then the 2-rank bench (torchrun)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader > gpurun_out/r02h_gpus.txt
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02h_all.log 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call I: out-of-line special path (parity + timing), panel-role clock vs number of panel CTAs
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export LPS_DEBUG=1
 timeout 900 python -m pytest tests/test_gpu_blocked.py -m gpu -x -q > gpurun_out/r02i_blocked.log 2>&1

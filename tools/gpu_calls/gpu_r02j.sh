@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call J (8 GPUs): multi-GPU parity tests, then the look-ahead loop at 8 / 4 / 2 / 1 ranks
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export LPS_DEBUG=1
 nvidia-smi --query-gpu=index,name --format=csv,noheader > gpurun_out/r02j_gpus.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call K (2 GPUs): panel role with two cells per thread + L2 eviction hints: parity, panel clock, N=2 bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export LPS_DEBUG=1
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r02k_all.log 2>&1
