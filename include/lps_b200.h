@@ -61,13 +61,16 @@ typedef struct {
                            5 = blocked loop (block_pivots pivots per tableau pass) with two launches per
                            pivot, 6 = blocked loop with one cooperative panel launch per block followed by
                            the pass, 7 = look-ahead blocked loop: ONE cooperative launch per block runs the
-                           pass of block k (out of place, TMA pipeline) and the panel of block k+1 side by
+                           pass of block k (out of place; TMA pipeline on shards >= 2.5 GB, cp.async pass
+                           below, update_variant >= 10 / 0..9 force either) and the panel of block k+1 side by
                            side on disjoint SMs (needs a second tableau buffer; the default above 64 MB), 8 = the same
                            with the pass warps and the panel warps inside every CTA (kb_step_ws) */
   int block_pivots;     /* lps_run: pivots deferred between two passes over the tableau (blocked loop):
                            0 = default (16), 1 = off (every pivot is its own pass), at most 20 (16 for
                            loop_mode 7).  Values are bit-identical for every setting. */
-  int panel_ctas;       /* loop_mode 7: CTAs (= SMs) given to the panel role, 0 = auto; the pass gets the rest */
+  int panel_ctas;       /* loop_mode 7: CTAs (= SMs) given to the panel role, the pass gets the rest; 0 = auto:
+                           lps_plan_split_model for a handle's first run, then re-fitted after every run from
+                           the two roles' measured durations (lps_plan_split_tuned) */
   int pass_chunk_rows;  /* TMA pass: rows per work chunk (rounded to a multiple of 12), 0 = auto */
   int reserved[3];
 } lps_options;
