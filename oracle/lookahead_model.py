@@ -70,7 +70,8 @@ class LookAheadModel:
             col_e = -(a / p)
             dst -= np.multiply.outer(a, r)
             dst[:, e] = col_e
-            dst[l, :] = r
+            if l >= 0:
+                dst[l, :] = r
         self.cur ^= 1
         self.passes += 1
 
@@ -83,20 +84,45 @@ class LookAheadModel:
                     x = -(a / p)
                 else:
                     x = x - a * r[j]
-                x[l] = r[j]
+                if l >= 0:                  # (-1: the leaving row lives on another rank)
+                    x[l] = r[j]
         return x
 
     @staticmethod
     def _replay_row(x, i, sets):
         for s in sets:
             for e, l, p, a, r in s.items():
-                if i == l:
+                if l >= 0 and i == l:
                     x = r.copy()
                 else:
                     xe = -(a[i] / p)
                     x = x - a[i] * r
                     x[e] = xe
         return x
+
+    # -- the two per-pivot decisions; a sharded rank overrides them with the exchanges --------------
+    def _leaving(self, a, bvec):
+        """ratio test over my rows on the RUNNING b (LPState.java:287-305) -> (row, pivot element)"""
+        best, l = self.inf, -1
+        ok = ~(a[:self.m] < self.eps)
+        with np.errstate(all="ignore"):
+            for i in np.nonzero(ok)[0]:
+                s = bvec[i] / a[i]
+                if s < best:
+                    best, l = s, int(i)
+        return best, l
+
+    def _decide(self, e, a, bvec):
+        """-> (global leaving row or -1, pivot element, my local index of that row or -1)"""
+        _, l = self._leaving(a, bvec) if e >= 0 else (self.inf, -1)
+        return l, (a[l] if l >= 0 else 0.0), l
+
+    def _pivot_row(self, Tread, l, lloc, p, e, sets):
+        """the scaled leaving row (LPState.java:137-146): replayed and scaled where the row lives
+        (l: global row, lloc: my local index of it)"""
+        r = self._replay_row(Tread[lloc, :].copy(), lloc, sets) / p
+        r[e] = 1.0 / p
+        return r
 
     def run(self, max_pivots: int = -1):
         """lps_run with loop_mode 7.  Returns (verdict, pivots)."""
@@ -114,36 +140,29 @@ class LookAheadModel:
             Tread = self.Tbuf[self.cur]        # both roles read it; the pass writes the other buffer
             own = _Set()
             while verdict is None and len(own) < self.block:
+                a = self._replay_column(Tread[:, e].copy(), e, (prev, own)) if e >= 0 else None      # phase A
+                l, p, lloc = self._decide(e, a, bvec)
                 if e < 0:
                     verdict = OPTIMAL
                     break
-                a = self._replay_column(Tread[:, e].copy(), e, (prev, own))      # phase A
-                ok = ~(a[:m] < self.eps)
-                best, l = self.inf, -1
-                with np.errstate(all="ignore"):
-                    for i in np.nonzero(ok)[0]:                                    # ratio test on the RUNNING b
-                        s = bvec[i] / a[i]
-                        if s < best:
-                            best, l = s, int(i)
                 if l < 0:
                     verdict = UNBOUNDED
                     break
                 if 0 <= max_pivots <= done:
                     verdict = PIVOT_CAP
                     break
-                p = a[l]
-                r = self._replay_row(Tread[l, :].copy(), l, (prev, own)) / p       # phase B, on the owner
-                r[e] = 1.0 / p
+                r = self._pivot_row(Tread, l, lloc, p, e, (prev, own))                                    # phase B
                 # running vectors: one multiply-subtract per entry (LPState.java:164 / :177)
                 rn, ce = r[n], a[m]
                 nb = bvec - a * rn
-                nb[l] = rn
+                if lloc >= 0:
+                    nb[lloc] = rn
                 nc = cvec - ce * r
                 nc[e] = -(ce / p)
                 # the objective slot is the same cell in both vectors: (m, n)
                 assert nb[m].tobytes() == nc[n].tobytes()
                 bvec, cvec = nb, nc
-                own.e.append(e); own.l.append(l); own.p.append(p); own.a.append(a); own.r.append(r)
+                own.e.append(e); own.l.append(lloc); own.p.append(p); own.a.append(a); own.r.append(r)
                 self.log.append((e, l))
                 done += 1
                 pos = np.nonzero(cvec[:n] > self.eps)[0]
@@ -177,3 +196,32 @@ class LookAheadModel:
     @property
     def v(self):
         return 0.0 - self.T[self.m, self.n]
+
+
+class ShardedLookAheadModel(LookAheadModel):
+    """One rank of the row-sharded look-ahead loop (kb_step<true, ...>): rows [lo, hi) of (A | b) plus a
+    replica of the objective row; the running b is local, the running c replicated.  Two callbacks stand
+    for what crosses NVLink per pivot in the product: `all_gather(obj) -> list` (the ratio-test candidates,
+    CTA 0's packets) and `broadcast(obj, src) -> obj` (the scaled pivot row, the owner's packets)."""
+
+    def __init__(self, A_local, b_local, c, lo, hi, m_total, owner_of, all_gather, broadcast, rank,
+                 v=0.0, block=16, eps=1e-9, inf=1e50):
+        super().__init__(A_local, b_local, c, v=v, block=block, eps=eps, inf=inf)
+        self.lo, self.hi, self.m_total = lo, hi, m_total
+        self.owner_of, self.all_gather, self.broadcast, self.rank = owner_of, all_gather, broadcast, rank
+
+    def _decide(self, e, a, bvec):
+        best, l_loc = self._leaving(a, bvec) if e >= 0 else (self.inf, -1)
+        cands = self.all_gather((float(best), self.lo + l_loc if l_loc >= 0 else -1,
+                                 float(a[l_loc]) if l_loc >= 0 else 0.0))
+        win = (self.inf, -1, 0.0)
+        for cand in cands:                    # lexicographic (ratio, global row): lowest row wins ties
+            if cand[1] >= 0 and (win[1] < 0 or cand[0] < win[0] or (cand[0] == win[0] and cand[1] < win[1])):
+                win = cand
+        l, p = win[1], win[2]
+        mine = l >= 0 and self.owner_of(l) == self.rank
+        return l, p, (l - self.lo if mine else -1)
+
+    def _pivot_row(self, Tread, l, lloc, p, e, sets):
+        r = super()._pivot_row(Tread, l, lloc, p, e, sets) if lloc >= 0 else None      # compute + broadcast on the owner
+        return np.asarray(self.broadcast(r, self.owner_of(l)))

@@ -148,6 +148,60 @@ def test_sharded_blocked_loop_equals_unsharded_oracle(world, m, n, seed, block):
         assert passes == -(-len(ref.log) // block)
 
 
+def _lookahead_worker(rank, world, port, m, n, seed, block, out_q):
+    """the row-sharded LOOK-AHEAD loop (oracle/lookahead_model.py) with gloo carrying the two exchanges"""
+    from oracle.lookahead_model import ShardedLookAheadModel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A, b, c = tier_f.gen_dense_feasible(m, n, seed)
+    lo, hi = partition(m, world, rank)
+
+    def all_gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    def broadcast(obj, src):
+        box = [obj]
+        dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+    mdl = ShardedLookAheadModel(A[lo:hi], b[lo:hi], c, lo, hi, m, lambda row: owner_of(row, m, world), all_gather,
+                                broadcast, rank, block=block)
+    mdl.run(7)                         # a capped run first: the next one starts from the other tableau buffer
+    status, k = mdl.run()
+    out_q.put((rank, mdl.log, mdl.A.copy(), mdl.b.copy(), mdl.c.copy(), mdl.v, mdl.passes, mdl.launches))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,m,n,seed,block", [(2, 14, 18, 0, 4), (2, 31, 20, 1, 16), (3, 25, 40, 2, 5)])
+def test_sharded_lookahead_loop_equals_unsharded_oracle(world, m, n, seed, block):
+    """the look-ahead loop on N GPUs (kb_step<true>: every rank's panel replays [previous block, own block] on
+    its rows of the not-yet-updated tableau, local running b, replicated running c, candidates all-gathered,
+    the owner replaying + scaling + broadcasting the leaving row) restated on the CPU over gloo: same pivots
+    and same cells as the unsharded binary64 oracle"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lookahead_worker, args=(r, world, port, m, n, seed, block, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    A, b, c = tier_f.gen_dense_feasible(m, n, seed)
+    ref = tier_f.TierFState(A, b, c)
+    ref.run()
+    for rank, log, Al, bl, cl, v, passes, launches in results:
+        lo, hi = partition(m, world, rank)
+        assert log == ref.log
+        assert np.array_equal(Al, ref.A[lo:hi]) and np.array_equal(bl, ref.b[lo:hi])
+        assert np.array_equal(cl, ref.c) and v == ref.v[0]
+        assert launches > passes
+
+
 @pytest.mark.parametrize("world,m,n,seed", [(2, 14, 18, 0), (2, 31, 20, 1), (3, 25, 40, 2)])
 def test_sharded_loop_equals_unsharded_oracle(world, m, n, seed):
     ctx = mp.get_context("spawn")
