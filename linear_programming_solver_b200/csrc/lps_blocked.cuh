@@ -47,17 +47,13 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// L2 eviction priorities (createpolicy): the tableau streams through the 126 MB L2 once per pass, the pending
-// columns / rows (a few MB) are re-read by every pivot of the panel, so the stream is marked evict_first and
-// the panel's operands evict_last
+// L2 eviction priority (createpolicy) for the tableau stream of the out-of-place pass: it goes through the 126 MB
+// L2 once per pass while the panel re-reads a few MB of pending columns / rows per pivot.  Off by default (env
+// LPS_L2_HINTS): neither this nor evict_last on the panel's operands nor an L2 persisting window measured a gain
+// (profiles/r02_summary.md).
 __device__ __forceinline__ unsigned long long l2_evict_first_policy() {
   unsigned long long p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 __device__ __forceinline__ D4 ld256_hint(const double* p, unsigned long long pol) {
@@ -71,10 +67,6 @@ __device__ __forceinline__ void st256_hint(double* p, const D4& v, unsigned long
   asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z),
                "d"(v.w), "l"(pol)
                : "memory");
-}
-__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gmem_src, unsigned long long pol) {
-  unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem_src), "l"(pol) : "memory");
 }
 constexpr int kColThreads = 128;
 constexpr int kPanelMax = 20;
