@@ -122,7 +122,11 @@ struct CtlS {
   unsigned int blk_ticket;    // last-CTA-done counter of kb_flush
   unsigned long long blk_queue;   // kb_flush: next unclaimed chunk
   unsigned long long bar_base;    // kb_panel: value of `bar` when the next cooperative launch starts
-  unsigned long long dbg_ns[16];   // kb_panel phase clock of CTA 0 (LPS_PANEL_TIMING builds only)
+  // role clocks (ns / counts), cleared by ks_begin_run.  Look-ahead step (lps_step.cuh): [0..5] the panel's phases,
+  // [10] pass durations, [11] passes, [12] / [13] the first launch's panel duration / pivots, [14] / [15] panel
+  // duration / pivots of the launches with a pass — read by the host to tune the SM split (tune_split, lps_api.cu)
+  // and printed with LPS_DEBUG=1.  kb_panel (LPS_PANEL_TIMING builds only): [0..13] phase clock of CTA 0.
+  unsigned long long dbg_ns[16];
   int blk_e2[2][kMaxBlock];   // [set][u] entering column of pending pivot u
   int blk_l2[2][kMaxBlock];   // its leaving row as a LOCAL row index, -1 if another rank owns the row
   double blk_p2[2][kMaxBlock];   // its pivot element
