@@ -101,3 +101,14 @@ def test_committed_digest_table_is_anchored_on_the_cpu_twin():
     # the driver's default runs land on committed checkpoints: (warmup + steps) * 256 pivots
     for warm, steps in [(3, 20), (5, 20), (3, 2), (1, 2)]:
         assert str((warm + steps) * 256) in tab["digests"]
+
+
+def test_committed_ncu_traffic_covers_every_bench_line():
+    """roofline.traffic comes from profiles/r02_traffic.json (ncu --set full captures, one per shard size):
+    every key bench.py / sharded.py ask for is there and within 10 % of the algorithmic bytes of that shard"""
+    for world in (1, 2, 4, 8):
+        t = bench.ncu_traffic("kb_step_n%d" % world)
+        algorithmic = 16 * (20000 // world + 1) * 40001
+        assert t is not None and 0.95 * algorithmic < t < 1.10 * algorithmic, (world, t, algorithmic)
+    assert bench.ncu_traffic("k_update_n1") is not None and bench.ncu_traffic("kb_step_c3") is not None
+    assert bench.ncu_traffic("no_such_kernel") is None
